@@ -1,0 +1,91 @@
+"""CPU: pin the oracle (oracle/plonk_oracle.py) against every golden vector the reference
+holds for the path: test.py commitment KAT + omega_8, three snarkjs verification
+keys, test/proof.pickle, Merlin's conformance vector, plus reference-generated fft/lincomb
+vectors (tests/golden/make_golden.py)."""
+import hashlib
+
+import pytest
+
+from oracle import plonk_oracle as O
+from tests.golden_io import (PTAU_HEAD, ints, load_circuit, load_json, proof_from_entry, pt)
+
+
+@pytest.fixture(scope="module")
+def setup():
+    return O.Setup.from_file(PTAU_HEAD)
+
+
+def test_merlin_conformance_vector():
+    t = O.MerlinTranscript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == load_json("circuits.json")["merlin_vector"]
+
+
+def test_transcript_vector():
+    g = load_json("circuits.json")["transcript"]
+    tr = O.Transcript(b"plonk")
+    tr.append_point(b"a_1", (1, 2))
+    tr.append_scalar(b"a_eval", 12345)
+    assert tr.get_and_append_challenge(b"beta") == int(g["beta"])
+    assert tr.get_and_append_challenge(b"gamma") == int(g["gamma"])
+
+
+def test_commit_kat_and_omega(setup):
+    """test.py:14-34."""
+    g = load_json("circuits.json")
+    assert setup.commit(ints(g["commit_kat"]["lagrange"])) == pt(g["commit_kat"]["point"])
+    assert setup.commit(list(range(1, 9))) == (
+        16120260411117808045030798560855586501988622612038310041007562782458075125622,
+        3125847109934958347271782137825877642397632921923926105820408033549219695465)
+    assert O.root_of_unity(8) == int(g["omega_8"])
+
+
+def test_fft_vectors():
+    for c in load_json("fft_vectors.json")["cases"]:
+        vals = ints(c["input"])
+        assert O.fft(vals) == ints(c["fft"])
+        assert O.ifft(vals) == ints(c["ifft"])
+        if "offset" in c and int(c["n"]) <= 64:
+            off = int(c["offset"])
+            assert O.to_coset_extended_lagrange(vals, off) == ints(c["coset_ext"])
+            assert O.coset_extended_lagrange_to_coeffs(vals, off) == ints(c["coset_to_coeffs"])
+            assert O.barycentric_eval(vals, int(c["x"])) == int(c["bary"])
+            assert O.barycentric_eval(vals, int(c["x_root"])) == int(c["bary_root"])
+
+
+def test_lincomb_vectors():
+    for c in load_json("lincomb_vectors.json")["cases"]:
+        pairs = list(zip([pt(p) for p in c["points"]], ints(c["scalars"])))
+        assert O.ec_lincomb(pairs) == pt(c["result"]), c["name"]
+        assert O.ec_lincomb_naive(pairs) == pt(c["result"]), c["name"]
+
+
+def test_lincomb_empty_raises():
+    with pytest.raises(ValueError):  # curve.py:93 max() of empty
+        O.ec_lincomb([])
+
+
+@pytest.mark.parametrize("name", ["basic", "ab_plus_a", "one_public"])
+def test_snarkjs_verification_keys(setup, name):
+    """test.py:37-100 -- keys produced by an independent implementation (snarkjs)."""
+    entry, arr = load_circuit(name)
+    assert entry["vk_kind"].startswith("reference")
+    pk = O.Preprocessed(entry["n"], *[arr[k] for k in ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3")])
+    vk = setup.verification_key(pk)
+    for k in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+        assert vk[k] == pt(entry["vk"][k]), k
+    assert vk["w"] == int(entry["vk"]["w"])
+
+
+@pytest.mark.parametrize("name", ["prover_test", "factorization"])
+def test_golden_proofs(setup, name):
+    """prover_test == test/proof.pickle (reference-published); factorization was accepted by
+    the reference's completed verifier when the fixture was generated."""
+    entry, arr = load_circuit(name)
+    pk = O.Preprocessed(entry["n"], *[arr[k] for k in ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3")])
+    proof = O.Prover(setup, pk).prove(arr["A"], arr["B"], arr["C"], ints(entry["public"]))
+    assert proof == proof_from_entry(entry)
+    assert hashlib.sha256(O.proof_bytes(proof)).hexdigest() == entry["proof_sha256"]
+    if name == "prover_test":
+        assert entry["proof_sha256"] == \
+            "4550f3296053d1b17252c41453680871b280af947381d270241c2957c730eeb1"
