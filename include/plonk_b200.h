@@ -1,0 +1,101 @@
+/* plonk_b200.h -- C ABI of libplonk_b200.so, the B200-native PLONK proving hot path.
+ *
+ * The reference (0xPARC/plonkathon) is pure Python and has no FFI of its own; these entry points are
+ * what a binding for its hot path would call, one per reference callable (file:line cited per entry,
+ * relative to the reference tree).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - Fr element  : 32 bytes, little-endian integer in [0, r), r = BN254 group order (curve.py:11).
+ *   - G1 affine   : 64 bytes, x || y, each a 32-byte little-endian integer in [0, q) (py_ecc FQ.n).
+ *                   The identity (py_ecc Z1 == None) is reported through an `is_identity` flag.
+ *   - "d_" pointers are device pointers on the context's device; "h_" pointers are host memory.
+ *   - Vectors at the ABI are in canonical (non-Montgomery) form unless a parameter says otherwise.
+ *   - Every call returns 0 on success, non-zero on error; pb200_last_error() describes the failure
+ *     (thread-local).  The Python facade turns errors into exceptions/AssertionErrors matching the
+ *     reference's behaviour.
+ *   - Work is issued on the context's CUDA stream; calls that return host data synchronise it.
+ */
+#ifndef PLONK_B200_H
+#define PLONK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb200_ctx pb200_ctx;
+typedef struct pb200_srs pb200_srs;
+typedef struct pb200_prover pb200_prover;
+typedef struct pb200_transcript pb200_transcript;
+
+/* ---- context ------------------------------------------------------------------------------- */
+const char* pb200_last_error(void);
+const char* pb200_version(void);
+/* cuda_stream may be NULL (the library creates its own non-blocking stream). */
+int pb200_ctx_create(int device, void* cuda_stream, pb200_ctx** out);
+void pb200_ctx_destroy(pb200_ctx* ctx);
+int pb200_ctx_sync(pb200_ctx* ctx);
+/* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t pb200_ctx_launches(pb200_ctx* ctx);
+/* the context's CUDA stream (cudaStream_t) so callers can time with events on it */
+void* pb200_ctx_stream(pb200_ctx* ctx);
+
+/* ---- Fr vectors ---------------------------------------------------------------------------- */
+/* canonical <-> Montgomery form, in place allowed */
+int pb200_fr_to_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n);
+int pb200_fr_from_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n);
+
+/* poly.py:113-149  Polynomial.fft(inv) / ifft: natural order in and out, n = 2^log_n <= 2^28.
+ * inverse != 0 uses the reversed roots and multiplies by n^-1.  d_out may alias d_in. */
+int pb200_fr_ntt(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse);
+int pb200_fr_ntt_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n, int inverse);
+
+/* poly.py:156-163  to_coset_extended_lagrange(offset): n Lagrange values -> 4n evaluations on
+ * offset * <w_4n>.  h_offset: 32-byte canonical Fr. */
+int pb200_fr_coset_extend(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset);
+int pb200_fr_coset_extend_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n,
+                               const uint8_t* h_offset);
+/* poly.py:169-177  coset_extended_lagrange_to_coeffs(offset): N values (N = 2^log_n, the extended size)
+ * -> N coefficients. */
+int pb200_fr_coset_to_coeffs(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset);
+int pb200_fr_coset_to_coeffs_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n,
+                                  const uint8_t* h_offset);
+/* poly.py:181-195  barycentric_eval(x) with py_ecc's inv(0) == 0 convention when x is on the domain. */
+int pb200_fr_barycentric_eval(pb200_ctx* ctx, const void* d_vals, unsigned log_n, const uint8_t* h_x, uint8_t* h_out);
+int pb200_fr_barycentric_eval_host(pb200_ctx* ctx, const uint8_t* h_vals, unsigned log_n, const uint8_t* h_x,
+                                   uint8_t* h_out);
+
+/* ---- G1 MSM -------------------------------------------------------------------------------- */
+/* curve.py:38-44  ec_lincomb(pairs): sum_i scalars[i] * points[i].  Points must be on the curve and not
+ * the identity (the facade drops None points); scalars already reduced mod r (curve.py:41).
+ * n == 0 is an error (the reference raises ValueError from max(), curve.py:93). */
+int pb200_g1_msm(pb200_ctx* ctx, const void* d_points, const void* d_scalars, uint64_t n, uint8_t* h_out_xy,
+                 int* is_identity);
+int pb200_g1_msm_host(pb200_ctx* ctx, const uint8_t* h_points, const uint8_t* h_scalars, uint64_t n,
+                      uint8_t* h_out_xy, int* is_identity);
+
+/* ---- SRS / Setup --------------------------------------------------------------------------- */
+/* setup.py:16-22  Setup.powers_of_x.  h_points: n affine points (canonical).  precompute != 0 builds the
+ * fixed-base window table in HBM (size ceil(256/c) * n * 64 bytes). */
+int pb200_srs_create(pb200_ctx* ctx, const uint8_t* h_points, uint64_t n, int precompute, pb200_srs** out);
+void pb200_srs_destroy(pb200_srs* srs);
+uint64_t pb200_srs_size(pb200_srs* srs);
+/* setup.py:66-72  Setup.commit(values): values in the LAGRANGE basis -> ifft -> MSM with powers_of_x.
+ * n = 2^log_n must be <= srs size. */
+int pb200_srs_commit_lagrange(pb200_ctx* ctx, pb200_srs* srs, const void* d_values, unsigned log_n,
+                              uint8_t* h_out_xy, int* is_identity);
+int pb200_srs_commit_lagrange_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t* h_values, unsigned log_n,
+                                   uint8_t* h_out_xy, int* is_identity);
+/* MSM of m coefficients (monomial basis) with the first m powers. */
+int pb200_srs_commit_coeffs(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m, int coeffs_montgomery,
+                            uint8_t* h_out_xy, int* is_identity);
+
+/* ---- micro-benchmarks (bench.py / profiles only) --------------------------------------------- */
+/* runs `iters` dependent Montgomery products per thread over `threads` threads; returns elapsed ms */
+int pb200_bench_modmul(pb200_ctx* ctx, int field /*0 Fr, 1 Fq*/, uint64_t threads, uint32_t iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONK_B200_H */

@@ -1,0 +1,122 @@
+"""ctypes binding of libplonk_b200.so (C ABI in include/plonk_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible when a
+context is requested, this module raises -- it never routes to another implementation."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplonk_b200.so")
+
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class PlonkB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise PlonkB200Error(
+            "libplonk_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`"
+            % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    V, I, U, U64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_uint64
+    P = ctypes.POINTER
+    sig = {
+        "pb200_last_error": (ctypes.c_char_p, []),
+        "pb200_version": (ctypes.c_char_p, []),
+        "pb200_ctx_create": (I, [I, V, P(V)]),
+        "pb200_ctx_destroy": (None, [V]),
+        "pb200_ctx_sync": (I, [V]),
+        "pb200_ctx_launches": (U64, [V]),
+        "pb200_ctx_stream": (V, [V]),
+        "pb200_fr_to_mont": (I, [V, V, V, U64]),
+        "pb200_fr_from_mont": (I, [V, V, V, U64]),
+        "pb200_fr_ntt": (I, [V, V, V, U, I]),
+        "pb200_fr_ntt_host": (I, [V, V, V, U, I]),
+        "pb200_fr_coset_extend": (I, [V, V, V, U, V]),
+        "pb200_fr_coset_extend_host": (I, [V, V, V, U, V]),
+        "pb200_fr_coset_to_coeffs": (I, [V, V, V, U, V]),
+        "pb200_fr_coset_to_coeffs_host": (I, [V, V, V, U, V]),
+        "pb200_fr_barycentric_eval": (I, [V, V, U, V, V]),
+        "pb200_fr_barycentric_eval_host": (I, [V, V, U, V, V]),
+        "pb200_g1_msm": (I, [V, V, V, U64, V, P(I)]),
+        "pb200_g1_msm_host": (I, [V, V, V, U64, V, P(I)]),
+        "pb200_srs_create": (I, [V, V, U64, I, P(V)]),
+        "pb200_srs_destroy": (None, [V]),
+        "pb200_srs_size": (U64, [V]),
+        "pb200_srs_commit_lagrange": (I, [V, V, V, U, V, P(I)]),
+        "pb200_srs_commit_lagrange_host": (I, [V, V, V, U, V, P(I)]),
+        "pb200_srs_commit_coeffs": (I, [V, V, V, U64, I, V, P(I)]),
+        "pb200_bench_modmul": (I, [V, I, U64, U, P(ctypes.c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib, tuple(sig)
+
+
+_lock = threading.Lock()
+_lib = None
+EXPORTS = ()
+
+
+def lib():
+    global _lib, EXPORTS
+    with _lock:
+        if _lib is None:
+            _lib, EXPORTS = _load()
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise PlonkB200Error(lib().pb200_last_error().decode())
+
+
+class Context:
+    """One per device (one process per GPU).  Owns the CUDA stream, NTT plans and scratch memory."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = ctypes.c_void_p()
+        check(lib().pb200_ctx_create(device, ctypes.c_void_p(stream), ctypes.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def sync(self):
+        check(lib().pb200_ctx_sync(self.handle))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().pb200_ctx_launches(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().pb200_ctx_stream(self.handle) or 0)
+
+    def close(self):
+        if self.handle:
+            lib().pb200_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    """Context on LOCAL_RANK's device (one process per GPU), created on first use."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx

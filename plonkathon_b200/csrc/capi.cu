@@ -1,0 +1,284 @@
+// extern "C" surface of libplonk_b200.so (declared in include/plonk_b200.h).
+#include "../../include/plonk_b200.h"
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pb200 {
+// ntt.cu
+void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in, const Fr* in_scale,
+             const Fr* out_scale);
+void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
+Fr fr_from_u64(uint64_t x);
+// poly_ops.cu
+void fr_to_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
+void fr_from_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
+void barycentric_eval(Context* ctx, const Fr* d_vals, int log_n, const Fr& x_mont, Fr* h_out);
+float bench_modmul(Context* ctx, int field, uint64_t threads, uint32_t iters);
+// msm.cu
+struct Srs;
+Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precompute);
+void srs_destroy(Srs* s);
+void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
+uint64_t srs_size(Srs* s);
+uint32_t msm_default_window(uint64_t n, bool fixed_base);
+void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
+             bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity);
+__global__ void k_affine_to_mont(const G1Affine* in, G1Affine* out, uint64_t n);
+}  // namespace pb200
+
+using namespace pb200;
+
+static thread_local std::string g_err;
+
+#define PB_API_BEGIN try {
+#define PB_API_END                        \
+  return 0;                               \
+  }                                       \
+  catch (const std::exception& e) {       \
+    g_err = e.what();                     \
+    return 1;                             \
+  }                                       \
+  catch (...) {                           \
+    g_err = "unknown error";              \
+    return 1;                             \
+  }
+
+static Context* C(pb200_ctx* c) { return reinterpret_cast<Context*>(c); }
+
+static Fr load_fr_canonical(const uint8_t* h) {
+  Fr a;
+  memcpy(a.v, h, 32);
+  // reject non-canonical input
+  Fr m = Fr::modulus();
+  bool lt = false;
+  for (int i = 7; i >= 0; i--) {
+    if (a.v[i] != m.v[i]) { lt = a.v[i] < m.v[i]; break; }
+  }
+  PB_CHECK(lt, "Fr value not reduced below the modulus");
+  return a;
+}
+
+extern "C" {
+
+const char* pb200_last_error(void) { return g_err.c_str(); }
+const char* pb200_version(void) { return "plonk_b200 0.1 (sm_100a)"; }
+
+int pb200_ctx_create(int device, void* cuda_stream, pb200_ctx** out) {
+  PB_API_BEGIN
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  PB_CHECK(e == cudaSuccess && count > 0, "no CUDA device: libplonk_b200 has no CPU fallback");
+  PB_CHECK(device >= 0 && device < count, "bad device ordinal");
+  PB_CUDA(cudaSetDevice(device));
+  auto ctx = std::make_unique<Context>();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  PB_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cuda_stream) {
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  } else {
+    PB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  *out = reinterpret_cast<pb200_ctx*>(ctx.release());
+  PB_API_END
+}
+
+void pb200_ctx_destroy(pb200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(C(ctx)->device);
+  cudaStreamSynchronize(C(ctx)->stream);
+  delete C(ctx);
+}
+
+int pb200_ctx_sync(pb200_ctx* ctx) {
+  PB_API_BEGIN
+  PB_CUDA(cudaStreamSynchronize(C(ctx)->stream));
+  PB_API_END
+}
+
+uint64_t pb200_ctx_launches(pb200_ctx* ctx) { return C(ctx)->launches; }
+void* pb200_ctx_stream(pb200_ctx* ctx) { return (void*)C(ctx)->stream; }
+
+int pb200_fr_to_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n) {
+  PB_API_BEGIN
+  fr_to_mont(C(ctx), (const Fr*)d_in, (Fr*)d_out, n);
+  PB_API_END
+}
+int pb200_fr_from_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n) {
+  PB_API_BEGIN
+  fr_from_mont(C(ctx), (const Fr*)d_in, (Fr*)d_out, n);
+  PB_API_END
+}
+
+int pb200_fr_ntt(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse) {
+  PB_API_BEGIN
+  ntt_run(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, inverse != 0, (uint64_t)1 << log_n, nullptr, nullptr);
+  PB_API_END
+}
+
+// staging helpers for the host-buffer entry points
+struct HostStage {
+  Context* ctx;
+  DevBuf in, out;
+  HostStage(Context* c, const uint8_t* h_in, size_t in_bytes, size_t out_bytes) : ctx(c), in(in_bytes), out(out_bytes) {
+    if (in_bytes) PB_CUDA(cudaMemcpyAsync(in.p, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  void finish(uint8_t* h_out, size_t bytes) {
+    PB_CUDA(cudaMemcpyAsync(h_out, out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+};
+
+int pb200_fr_ntt_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n, int inverse) {
+  PB_API_BEGIN
+  size_t bytes = ((size_t)1 << log_n) * 32;
+  HostStage st(C(ctx), h_in, bytes, bytes);
+  ntt_run(C(ctx), st.in.as<Fr>(), st.out.as<Fr>(), (int)log_n, inverse != 0, (uint64_t)1 << log_n, nullptr, nullptr);
+  st.finish(h_out, bytes);
+  PB_API_END
+}
+
+// poly.py:156-163: ifft(n) ; coefficient i *= offset^i ; zero-pad to 4n ; fft(4n)
+static void coset_extend(Context* ctx, const Fr* d_in, Fr* d_out, int log_n, const uint8_t* h_offset) {
+  uint64_t n = (uint64_t)1 << log_n;
+  Fr off = fp_to_mont(load_fr_canonical(h_offset));
+  DevBuf coeffs(n * 32), powers(n * 32);
+  ntt_run(ctx, d_in, coeffs.as<Fr>(), log_n, true, n, nullptr, nullptr);
+  launch_powers(ctx, powers.as<Fr>(), n, off, Fr::one());
+  ntt_run(ctx, coeffs.as<Fr>(), d_out, log_n + 2, false, n, powers.as<Fr>(), nullptr);
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));  // temporaries die here
+}
+
+// poly.py:169-177: ifft(N) ; coefficient i *= offset^-i
+static void coset_to_coeffs(Context* ctx, const Fr* d_in, Fr* d_out, int log_n, const uint8_t* h_offset) {
+  uint64_t n = (uint64_t)1 << log_n;
+  Fr off = fp_to_mont(load_fr_canonical(h_offset));
+  Fr inv = fp_inv(off);  // inv(0) == 0 like py_ecc
+  DevBuf powers(n * 32);
+  launch_powers(ctx, powers.as<Fr>(), n, inv, Fr::one());
+  ntt_run(ctx, d_in, d_out, log_n, true, n, nullptr, powers.as<Fr>());
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int pb200_fr_coset_extend(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset) {
+  PB_API_BEGIN
+  coset_extend(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, h_offset);
+  PB_API_END
+}
+int pb200_fr_coset_extend_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n,
+                               const uint8_t* h_offset) {
+  PB_API_BEGIN
+  size_t bytes = ((size_t)1 << log_n) * 32;
+  HostStage st(C(ctx), h_in, bytes, bytes * 4);
+  coset_extend(C(ctx), st.in.as<Fr>(), st.out.as<Fr>(), (int)log_n, h_offset);
+  st.finish(h_out, bytes * 4);
+  PB_API_END
+}
+int pb200_fr_coset_to_coeffs(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset) {
+  PB_API_BEGIN
+  coset_to_coeffs(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, h_offset);
+  PB_API_END
+}
+int pb200_fr_coset_to_coeffs_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n,
+                                  const uint8_t* h_offset) {
+  PB_API_BEGIN
+  size_t bytes = ((size_t)1 << log_n) * 32;
+  HostStage st(C(ctx), h_in, bytes, bytes);
+  coset_to_coeffs(C(ctx), st.in.as<Fr>(), st.out.as<Fr>(), (int)log_n, h_offset);
+  st.finish(h_out, bytes);
+  PB_API_END
+}
+
+int pb200_fr_barycentric_eval(pb200_ctx* ctx, const void* d_vals, unsigned log_n, const uint8_t* h_x, uint8_t* h_out) {
+  PB_API_BEGIN
+  Fr x = fp_to_mont(load_fr_canonical(h_x));
+  Fr r;
+  barycentric_eval(C(ctx), (const Fr*)d_vals, (int)log_n, x, &r);
+  memcpy(h_out, r.v, 32);
+  PB_API_END
+}
+int pb200_fr_barycentric_eval_host(pb200_ctx* ctx, const uint8_t* h_vals, unsigned log_n, const uint8_t* h_x,
+                                   uint8_t* h_out) {
+  PB_API_BEGIN
+  size_t bytes = ((size_t)1 << log_n) * 32;
+  HostStage st(C(ctx), h_vals, bytes, 0);
+  Fr x = fp_to_mont(load_fr_canonical(h_x));
+  Fr r;
+  barycentric_eval(C(ctx), st.in.as<Fr>(), (int)log_n, x, &r);
+  memcpy(h_out, r.v, 32);
+  PB_API_END
+}
+
+int pb200_g1_msm(pb200_ctx* ctx, const void* d_points, const void* d_scalars, uint64_t n, uint8_t* h_out_xy,
+                 int* is_identity) {
+  PB_API_BEGIN
+  PB_CHECK(n > 0, "ec_lincomb of an empty list (the reference raises ValueError, curve.py:93)");
+  Context* c = C(ctx);
+  DevBuf mont(n * sizeof(G1Affine));
+  k_affine_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const G1Affine*)d_points, mont.as<G1Affine>(), n);
+  c->launches++;
+  msm_run(c, mont.as<G1Affine>(), n, (const Fr*)d_scalars, false, msm_default_window(n, false), false, 0, h_out_xy,
+          is_identity);
+  PB_API_END
+}
+
+int pb200_g1_msm_host(pb200_ctx* ctx, const uint8_t* h_points, const uint8_t* h_scalars, uint64_t n,
+                      uint8_t* h_out_xy, int* is_identity) {
+  PB_API_BEGIN
+  PB_CHECK(n > 0, "ec_lincomb of an empty list (the reference raises ValueError, curve.py:93)");
+  Context* c = C(ctx);
+  DevBuf pts(n * 64), sc(n * 32);
+  PB_CUDA(cudaMemcpyAsync(pts.p, h_points, n * 64, cudaMemcpyHostToDevice, c->stream));
+  PB_CUDA(cudaMemcpyAsync(sc.p, h_scalars, n * 32, cudaMemcpyHostToDevice, c->stream));
+  int rc = pb200_g1_msm(ctx, pts.p, sc.p, n, h_out_xy, is_identity);
+  if (rc) throw Error(g_err);
+  PB_API_END
+}
+
+int pb200_srs_create(pb200_ctx* ctx, const uint8_t* h_points, uint64_t n, int precompute, pb200_srs** out) {
+  PB_API_BEGIN
+  PB_CHECK(n > 0, "empty SRS");
+  *out = reinterpret_cast<pb200_srs*>(srs_create(C(ctx), h_points, n, precompute));
+  PB_API_END
+}
+void pb200_srs_destroy(pb200_srs* srs) { srs_destroy(reinterpret_cast<Srs*>(srs)); }
+uint64_t pb200_srs_size(pb200_srs* srs) { return srs_size(reinterpret_cast<Srs*>(srs)); }
+
+int pb200_srs_commit_lagrange(pb200_ctx* ctx, pb200_srs* srs, const void* d_values, unsigned log_n, uint8_t* h_out_xy,
+                              int* is_identity) {
+  PB_API_BEGIN
+  Context* c = C(ctx);
+  uint64_t n = (uint64_t)1 << log_n;
+  PB_CHECK(n <= srs_size(reinterpret_cast<Srs*>(srs)), "Not enough powers in setup");
+  DevBuf coeffs(n * 32);
+  ntt_run(c, (const Fr*)d_values, coeffs.as<Fr>(), (int)log_n, true, n, nullptr, nullptr);
+  srs_msm(c, reinterpret_cast<Srs*>(srs), coeffs.as<Fr>(), n, false, h_out_xy, is_identity);
+  PB_API_END
+}
+int pb200_srs_commit_lagrange_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t* h_values, unsigned log_n,
+                                   uint8_t* h_out_xy, int* is_identity) {
+  PB_API_BEGIN
+  size_t bytes = ((size_t)1 << log_n) * 32;
+  HostStage st(C(ctx), h_values, bytes, 0);
+  int rc = pb200_srs_commit_lagrange(ctx, srs, st.in.p, log_n, h_out_xy, is_identity);
+  if (rc) throw Error(g_err);
+  PB_API_END
+}
+int pb200_srs_commit_coeffs(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m, int coeffs_montgomery,
+                            uint8_t* h_out_xy, int* is_identity) {
+  PB_API_BEGIN
+  srs_msm(C(ctx), reinterpret_cast<Srs*>(srs), (const Fr*)d_coeffs, m, coeffs_montgomery != 0, h_out_xy, is_identity);
+  PB_API_END
+}
+
+int pb200_bench_modmul(pb200_ctx* ctx, int field, uint64_t threads, uint32_t iters, float* ms_out) {
+  PB_API_BEGIN
+  *ms_out = bench_modmul(C(ctx), field, threads, iters);
+  PB_API_END
+}
+
+}  // extern "C"

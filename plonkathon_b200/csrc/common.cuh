@@ -1,0 +1,81 @@
+// Shared host-side plumbing for libplonk_b200.so: error handling, the per-device context.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "curve.cuh"
+#include "field.cuh"
+
+namespace pb200 {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define PB_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      char b__[512];                                                                           \
+      snprintf(b__, sizeof b__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+               __FILE__, __LINE__);                                                            \
+      throw pb200::Error(b__);                                                                 \
+    }                                                                                          \
+  } while (0)
+
+#define PB_CHECK(cond, msg)                                                                    \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      char b__[512];                                                                           \
+      snprintf(b__, sizeof b__, "%s (%s:%d)", msg, __FILE__, __LINE__);                        \
+      throw pb200::Error(b__);                                                                 \
+    }                                                                                          \
+  } while (0)
+
+// owning device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n) PB_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void ensure(size_t n) { if (n > bytes) alloc(n); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct NttPlan;
+struct Srs;
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  std::map<int, std::unique_ptr<NttPlan>> plans;  // key: log_n * 2 + inverse
+  DevBuf scratch[8];                               // reusable temporaries
+  uint64_t launches = 0;                           // kernels launched through this context
+  ~Context();
+};
+
+NttPlan* get_plan(Context* ctx, int log_n, bool inverse);
+
+}  // namespace pb200

@@ -1,0 +1,369 @@
+// G1 multi-scalar multiplication (Pippenger / bucket method) for sm_100a.
+//
+// Replaces curve.py:38-111 (`ec_lincomb` -> `lincomb` -> `multisubset`) and the MSM half of
+// setup.py:66-72 (`Setup.commit`).  The result sum_i s_i * P_i is algorithm-independent, so the
+// reference's bit-sliced power-set method is replaced by:
+//   1. signed-digit window slicing of every scalar (c-bit windows, digits in [-2^(c-1), 2^(c-1)]),
+//      with a global histogram of bucket loads                                  (k_msm_digits)
+//   2. exclusive scan of the histogram                                           (k_scan_u32)
+//   3. counting-sort scatter of (point index, sign) by bucket                    (k_msm_scatter)
+//   4. bucket accumulation: XYZZ accumulator += affine point (8M+2S, no inversion) (k_msm_accumulate)
+//   5. bucket reduction sum_b (b+1) * B_b by running sums over bucket groups     (k_bucket_groups)
+//      followed by a tree sum of the group results                               (k_sum_points)
+//   6. the few remaining group operations (window Horner, one inversion to affine) on the host,
+//      which has to read the point anyway to feed the Fiat-Shamir transcript.
+// Two modes: "generic" (arbitrary points: W windows x 2^(c-1) buckets) and "fixed-base" (SRS with the
+// window multiples 2^(c*w) * P_i precomputed in HBM: one shared set of 2^(c-1) buckets, no Horner).
+#include "common.cuh"
+
+namespace pb200 {
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ G1Affine ld_affine(const G1Affine* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  G1Affine r;
+  r.x.v[0] = a.x; r.x.v[1] = a.y; r.x.v[2] = a.z; r.x.v[3] = a.w;
+  r.x.v[4] = b.x; r.x.v[5] = b.y; r.x.v[6] = b.z; r.x.v[7] = b.w;
+  r.y.v[0] = c.x; r.y.v[1] = c.y; r.y.v[2] = c.z; r.y.v[3] = c.w;
+  r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
+  return r;
+}
+
+struct MsmGeom {
+  uint32_t c, W;            // window bits, number of windows
+  uint32_t half;            // 2^(c-1) buckets per window
+  uint32_t bucket_stride;   // generic: half ; fixed-base: 0
+  uint64_t point_stride;    // generic: 0 ; fixed-base: n (index of window w's copy of point i = w*n + i)
+  uint32_t nb;              // total buckets
+};
+
+// ---- signed-digit walk shared by the histogram and scatter passes
+struct DigitWalk {
+  Fr s;
+  uint32_t carry;
+  __device__ __forceinline__ DigitWalk(const Fr* scalars, uint64_t i, int from_mont) : carry(0) {
+    s = scalars[i];
+    if (from_mont) s = fp_from_mont(s);
+  }
+  // digit of window w as (magnitude d in [0, 2^(c-1)], sign)
+  __device__ __forceinline__ uint32_t next(uint32_t w, const MsmGeom& g, uint32_t& neg) {
+    uint32_t bit = w * g.c;
+    uint32_t limb = bit >> 5, off = bit & 31;
+    uint64_t two = limb < 8 ? s.v[limb] : 0;
+    if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+    uint32_t raw = (uint32_t)(two >> off) & ((1u << g.c) - 1);
+    uint32_t d = raw + carry;
+    neg = 0;
+    if (d > g.half) { d = (1u << g.c) - d; neg = 1; carry = 1; } else carry = 0;
+    return d;
+  }
+};
+
+// counts[bucket]++ for every non-zero digit
+__global__ void k_msm_histogram(const Fr* scalars, uint64_t n, int from_mont, MsmGeom g, uint32_t* counts) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DigitWalk dw(scalars, i, from_mont);
+  for (uint32_t w = 0; w < g.W; w++) {
+    uint32_t neg, d = dw.next(w, g, neg);
+    if (d) atomicAdd(&counts[w * g.bucket_stride + (d - 1)], 1u);
+  }
+}
+
+// single-block exclusive scan: offsets[0..nb] from counts[0..nb-1]; also zeroes counts (reused as cursors)
+__global__ void k_scan_u32(uint32_t* counts, uint32_t* offsets, uint32_t nb) {
+  __shared__ uint32_t part[1024];
+  uint32_t tid = threadIdx.x;
+  uint32_t per = (nb + 1023) / 1024;
+  uint32_t lo = tid * per, hi = min(lo + per, nb);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += counts[i];
+  part[tid] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 1024; d <<= 1) {
+    uint32_t v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = tid ? part[tid - 1] : 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    uint32_t c = counts[i];
+    offsets[i] = run;
+    run += c;
+    counts[i] = 0;
+  }
+  if (tid == 1023) offsets[nb] = part[1023];
+}
+
+// sorted[offsets[key] + cursor++] = point index | sign << 31
+__global__ void k_msm_scatter(const Fr* scalars, uint64_t n, int from_mont, MsmGeom g, const uint32_t* offsets,
+                              uint32_t* cursors, uint32_t* sorted) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  DigitWalk dw(scalars, i, from_mont);
+  for (uint32_t w = 0; w < g.W; w++) {
+    uint32_t neg, d = dw.next(w, g, neg);
+    if (d) {
+      uint32_t key = w * g.bucket_stride + (d - 1);
+      uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
+      sorted[pos] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
+    }
+  }
+}
+
+// one thread per bucket: B_b = sum of its (signed) points
+__global__ void __launch_bounds__(128) k_msm_accumulate(const G1Affine* points, const uint32_t* offsets,
+                                                        const uint32_t* sorted, uint32_t nb, G1XYZZ* buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  uint32_t lo = offsets[b], hi = offsets[b + 1];
+  G1XYZZ acc = G1XYZZ::identity();
+  for (uint32_t e = lo; e < hi; e++) {
+    uint32_t v = sorted[e];
+    G1Affine p = ld_affine(points + (v & 0x7fffffffu));
+    if (v >> 31) p.y = fp_neg(p.y);
+    g1_add_mixed(acc, p);
+  }
+  buckets[b] = acc;
+}
+
+// acc = k * p (k < 2^31), double-and-add from the top bit
+__device__ G1XYZZ g1_mul_small(const G1XYZZ& p, uint32_t k) {
+  G1XYZZ r = G1XYZZ::identity();
+  for (int i = 31; i >= 0; i--) {
+    g1_double(r);
+    if ((k >> i) & 1) g1_add(r, p);
+  }
+  return r;
+}
+
+// group t covers bucket indices [lo, lo+gsz) of one window; out[t] = sum_{idx} (idx_in_window + 1) * B
+__global__ void __launch_bounds__(128) k_bucket_groups(const G1XYZZ* buckets, uint32_t half, uint32_t gsz,
+                                                       uint32_t n_groups_total, G1XYZZ* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_groups_total) return;
+  uint32_t groups_per_window = half / gsz;
+  uint32_t w = t / groups_per_window, gi = t % groups_per_window;
+  uint32_t lo = gi * gsz;
+  const G1XYZZ* base = buckets + (uint64_t)w * half + lo;
+  G1XYZZ acc = G1XYZZ::identity(), sum = G1XYZZ::identity();
+  for (int k = (int)gsz - 1; k >= 0; k--) {
+    G1XYZZ bk = base[k];
+    g1_add(acc, bk);
+    g1_add(sum, acc);
+  }
+  if (lo) {
+    G1XYZZ m = g1_mul_small(acc, lo);
+    g1_add(sum, m);
+  }
+  out[t] = sum;
+}
+
+// out[w] = sum of in[w * per + 0 .. per)   (one block per w)
+__global__ void __launch_bounds__(128) k_sum_points(const G1XYZZ* in, uint32_t per, G1XYZZ* out) {
+  __shared__ G1XYZZ sh[128];
+  const G1XYZZ* base = in + (uint64_t)blockIdx.x * per;
+  G1XYZZ acc = G1XYZZ::identity();
+  for (uint32_t i = threadIdx.x; i < per; i += blockDim.x) {
+    G1XYZZ v = base[i];
+    g1_add(acc, v);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+    if (threadIdx.x < d) {
+      G1XYZZ a = sh[threadIdx.x], b = sh[threadIdx.x + d];
+      g1_add(a, b);
+      sh[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+
+// affine points: canonical <-> Montgomery (both coordinates)
+__global__ void k_affine_to_mont(const G1Affine* in, G1Affine* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = in[i];
+  p.x = fp_to_mont(p.x);
+  p.y = fp_to_mont(p.y);
+  out[i] = p;
+}
+
+// out[i] = 2^c * in[i] as XYZZ
+__global__ void __launch_bounds__(128) k_window_step(const G1Affine* in, G1XYZZ* out, uint64_t n, uint32_t c) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = in[i];
+  G1XYZZ a;
+  g1_double_affine(a, p);
+  for (uint32_t k = 1; k < c; k++) g1_double(a);
+  out[i] = a;
+}
+
+// XYZZ -> affine with Montgomery's batch-inversion trick, CH points per thread (none is the identity)
+__global__ void __launch_bounds__(128) k_batch_to_affine(const G1XYZZ* in, G1Affine* out, uint64_t n) {
+  const int CH = 16;
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i0 = t * CH;
+  if (i0 >= n) return;
+  int cnt = (int)min((uint64_t)CH, n - i0);
+  Fq pref[CH];
+  Fq run = Fq::one();
+  for (int k = 0; k < cnt; k++) {
+    pref[k] = run;                      // product of ZZZ[0..k)
+    run = fp_mul(run, in[i0 + k].ZZZ);
+  }
+  Fq inv = fp_inv(run);
+  for (int k = cnt - 1; k >= 0; k--) {
+    G1XYZZ a = in[i0 + k];
+    Fq A = fp_mul(inv, pref[k]);        // 1 / ZZZ_k
+    inv = fp_mul(inv, a.ZZZ);
+    Fq izz = fp_sqr(fp_mul(a.ZZ, A));
+    G1Affine p;
+    p.x = fp_mul(a.X, izz);
+    p.y = fp_mul(a.Y, A);
+    out[i0 + k] = p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+struct Srs {
+  uint64_t n = 0;
+  DevBuf base;       // n affine points, Montgomery form
+  uint32_t c = 0, W = 0;
+  DevBuf expanded;   // W * n affine points (window multiples), or empty
+};
+
+static uint32_t windows_for(uint32_t c) { return (256 + c - 1) / c; }
+
+uint32_t msm_default_window(uint64_t n, bool fixed_base) {
+  int lg = 0;
+  while (((uint64_t)1 << lg) < n) lg++;
+  int c = fixed_base ? lg : lg - 4;
+  int lo = 4, hi = fixed_base ? 21 : 16;
+  if (const char* e = getenv(fixed_base ? "PB200_MSM_C_FIXED" : "PB200_MSM_C")) { c = atoi(e); }
+  if (c < lo) c = lo;
+  if (c > hi) c = hi;
+  return (uint32_t)c;
+}
+
+static void host_horner_to_affine(const std::vector<G1XYZZ>& ws, uint32_t c, uint8_t* out_xy, int* is_identity) {
+  G1XYZZ r = G1XYZZ::identity();
+  for (int w = (int)ws.size() - 1; w >= 0; w--) {
+    if (w != (int)ws.size() - 1)
+      for (uint32_t k = 0; k < c; k++) g1_double(r);
+    g1_add(r, ws[w]);
+  }
+  G1Affine a;
+  bool inf = g1_to_affine(r, a);
+  *is_identity = inf ? 1 : 0;
+  Fq x = fp_from_mont(a.x), y = fp_from_mont(a.y);
+  memcpy(out_xy, x.v, 32);
+  memcpy(out_xy + 32, y.v, 32);
+}
+
+// points: Montgomery affine (generic: n points; fixed-base: expanded table W*n).
+void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
+             bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity) {
+  PB_CHECK(n > 0, "empty MSM");
+  MsmGeom g;
+  g.c = c;
+  g.W = windows_for(c);
+  g.half = 1u << (c - 1);
+  g.bucket_stride = fixed_base ? 0 : g.half;
+  g.point_stride = fixed_base ? point_stride : 0;
+  g.nb = fixed_base ? g.half : g.half * g.W;
+  PB_CHECK((fixed_base ? (uint64_t)g.W * point_stride : n) < (1ull << 31), "MSM too large for 31-bit point ids");
+  uint32_t n_windows_out = fixed_base ? 1 : g.W;
+
+  DevBuf& sorted = ctx->scratch[2];
+  DevBuf& counts = ctx->scratch[3];
+  DevBuf& offsets = ctx->scratch[4];
+  DevBuf& buckets = ctx->scratch[5];
+  DevBuf& groups = ctx->scratch[6];
+  DevBuf& wsums = ctx->scratch[7];
+  uint64_t entries = n * g.W;
+  sorted.ensure(entries * 4);
+  counts.ensure((size_t)g.nb * 4);
+  offsets.ensure((size_t)(g.nb + 1) * 4);
+  buckets.ensure((size_t)g.nb * sizeof(G1XYZZ));
+  uint32_t gsz = g.half >= 64 ? 64 : g.half;
+  uint32_t n_groups = g.nb / gsz;
+  groups.ensure((size_t)n_groups * sizeof(G1XYZZ));
+  wsums.ensure((size_t)n_windows_out * sizeof(G1XYZZ));
+
+  cudaStream_t st = ctx->stream;
+  PB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)g.nb * 4, st));
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  k_msm_histogram<<<blocks, 128, 0, st>>>(scalars, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
+  k_scan_u32<<<1, 1024, 0, st>>>(counts.as<uint32_t>(), offsets.as<uint32_t>(), g.nb);
+  k_msm_scatter<<<blocks, 128, 0, st>>>(scalars, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
+                                        counts.as<uint32_t>(), sorted.as<uint32_t>());
+  k_msm_accumulate<<<(g.nb + 127) / 128, 128, 0, st>>>(points, offsets.as<uint32_t>(), sorted.as<uint32_t>(), g.nb,
+                                                      buckets.as<G1XYZZ>());
+  k_bucket_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(buckets.as<G1XYZZ>(), g.half, gsz, n_groups,
+                                                         groups.as<G1XYZZ>());
+  k_sum_points<<<n_windows_out, 128, 0, st>>>(groups.as<G1XYZZ>(), g.half / gsz, wsums.as<G1XYZZ>());
+  ctx->launches += 6;
+  PB_CUDA(cudaGetLastError());
+  std::vector<G1XYZZ> ws(n_windows_out);
+  PB_CUDA(cudaMemcpyAsync(ws.data(), wsums.p, n_windows_out * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  host_horner_to_affine(ws, c, out_xy, is_identity);
+}
+
+// ---- SRS --------------------------------------------------------------------------------
+// h_points: n affine points, canonical little-endian (x || y), none the identity
+Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precompute) {
+  auto srs = std::make_unique<Srs>();
+  srs->n = n;
+  srs->base.alloc(n * sizeof(G1Affine));
+  DevBuf raw(n * sizeof(G1Affine));
+  PB_CUDA(cudaMemcpyAsync(raw.p, h_points, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+  k_affine_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(raw.as<G1Affine>(), srs->base.as<G1Affine>(), n);
+  ctx->launches++;
+  if (precompute) {
+    uint32_t c = msm_default_window(n, true);
+    uint32_t W = windows_for(c);
+    srs->c = c;
+    srs->W = W;
+    srs->expanded.alloc((size_t)W * n * sizeof(G1Affine));
+    G1Affine* ex = srs->expanded.as<G1Affine>();
+    PB_CUDA(cudaMemcpyAsync(ex, srs->base.p, n * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream));
+    DevBuf tmp(n * sizeof(G1XYZZ));
+    for (uint32_t w = 1; w < W; w++) {
+      k_window_step<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ex + (uint64_t)(w - 1) * n, tmp.as<G1XYZZ>(), n, c);
+      uint64_t threads = (n + 15) / 16;
+      k_batch_to_affine<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(tmp.as<G1XYZZ>(), ex + (uint64_t)w * n, n);
+      ctx->launches += 2;
+    }
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  PB_CUDA(cudaGetLastError());
+  return srs.release();
+}
+
+void srs_destroy(Srs* s) { delete s; }
+
+// commit to m <= n coefficients (device, Montgomery or canonical form)
+void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity) {
+  PB_CHECK(m <= srs->n, "Not enough powers in setup");
+  if (srs->expanded.p) {
+    msm_run(ctx, srs->expanded.as<G1Affine>(), m, d_scalars, scalars_mont, srs->c, true, srs->n, out_xy, is_identity);
+  } else {
+    msm_run(ctx, srs->base.as<G1Affine>(), m, d_scalars, scalars_mont, msm_default_window(m, false), false, 0, out_xy,
+            is_identity);
+  }
+}
+
+uint64_t srs_size(Srs* s) { return s->n; }
+const G1Affine* srs_base(Srs* s) { return s->base.as<G1Affine>(); }
+
+}  // namespace pb200

@@ -1,0 +1,140 @@
+"""Drop-in for the reference's ``poly.py``: ``Basis`` and ``Polynomial`` with the same methods,
+assertions and list-of-Scalar ``.values`` (poly.py:10-195).  The transforms run on the GPU
+(csrc/ntt.cu) through the host-buffer C ABI; element-wise ring ops stay list-based like the
+reference (they are not on the accelerated path -- the prover uses device-resident vectors)."""
+from __future__ import annotations
+
+import ctypes
+from enum import Enum
+from typing import Optional
+
+from . import _lib
+from .curve import Scalar
+from .field import CURVE_ORDER
+
+
+class Basis(Enum):
+    LAGRANGE = 1
+    MONOMIAL = 2
+
+
+def _log2_exact(n: int) -> int:
+    assert n >= 1 and n & (n - 1) == 0, "length must be a power of two"
+    return n.bit_length() - 1
+
+
+def scalars_to_bytes(values) -> bytes:
+    return b"".join(v.n.to_bytes(32, "little") for v in values)
+
+
+def bytes_to_scalars(raw: bytes):
+    new = Scalar.__new__
+    out = []
+    for i in range(0, len(raw), 32):
+        s = new(Scalar)
+        s.n = int.from_bytes(raw[i:i + 32], "little")
+        out.append(s)
+    return out
+
+
+class Polynomial:
+    def __init__(self, values, basis: Basis):
+        assert all(isinstance(x, Scalar) for x in values)
+        assert isinstance(basis, Basis)
+        self.values = values
+        self.basis = basis
+
+    def __eq__(self, other):
+        return (self.basis == other.basis) and (self.values == other.values)
+
+    # ---- ring operations (poly.py:23-100)
+    def _zip(self, other, op, lagrange_only=False):
+        assert len(self.values) == len(other.values)
+        assert self.basis == other.basis
+        if lagrange_only:
+            assert self.basis == Basis.LAGRANGE
+        return Polynomial([op(x, y) for x, y in zip(self.values, other.values)], self.basis)
+
+    def __add__(self, other):
+        if isinstance(other, Polynomial):
+            return self._zip(other, lambda x, y: x + y)
+        assert isinstance(other, Scalar)
+        if self.basis == Basis.LAGRANGE:
+            return Polynomial([x + other for x in self.values], self.basis)
+        return Polynomial([self.values[0] + other] + self.values[1:], self.basis)
+
+    def __sub__(self, other):
+        if isinstance(other, Polynomial):
+            return self._zip(other, lambda x, y: x - y)
+        assert isinstance(other, Scalar)
+        if self.basis == Basis.LAGRANGE:
+            return Polynomial([x - other for x in self.values], self.basis)
+        return Polynomial([self.values[0] - other] + self.values[1:], self.basis)
+
+    def __mul__(self, other):
+        if isinstance(other, Polynomial):
+            return self._zip(other, lambda x, y: x * y, lagrange_only=True)
+        assert isinstance(other, Scalar)
+        return Polynomial([x * other for x in self.values], self.basis)
+
+    def __truediv__(self, other):
+        if isinstance(other, Polynomial):
+            return self._zip(other, lambda x, y: x / y, lagrange_only=True)
+        assert isinstance(other, Scalar)
+        return Polynomial([x / other for x in self.values], self.basis)
+
+    def shift(self, shift: int):
+        assert self.basis == Basis.LAGRANGE
+        assert shift < len(self.values)
+        return Polynomial(self.values[shift:] + self.values[:shift], self.basis)
+
+    # ---- transforms (GPU)
+    def _ctx(self, ctx):
+        return ctx or _lib.default_context()
+
+    def fft(self, inv=False, ctx: Optional[_lib.Context] = None):
+        """poly.py:113-145."""
+        if inv:
+            assert self.basis == Basis.LAGRANGE
+        else:
+            assert self.basis == Basis.MONOMIAL
+        n = len(self.values)
+        log_n = _log2_exact(n)
+        raw = scalars_to_bytes(self.values)
+        out = ctypes.create_string_buffer(len(raw))
+        _lib.check(_lib.lib().pb200_fr_ntt_host(self._ctx(ctx).handle, raw, out, log_n, 1 if inv else 0))
+        return Polynomial(bytes_to_scalars(out.raw), Basis.MONOMIAL if inv else Basis.LAGRANGE)
+
+    def ifft(self, ctx=None):
+        """poly.py:147-148."""
+        return self.fft(True, ctx)
+
+    def to_coset_extended_lagrange(self, offset, ctx=None):
+        """poly.py:156-163."""
+        assert self.basis == Basis.LAGRANGE
+        n = len(self.values)
+        raw = scalars_to_bytes(self.values)
+        out = ctypes.create_string_buffer(4 * len(raw))
+        off = (int(offset) % CURVE_ORDER).to_bytes(32, "little")
+        _lib.check(_lib.lib().pb200_fr_coset_extend_host(self._ctx(ctx).handle, raw, out, _log2_exact(n), off))
+        return Polynomial(bytes_to_scalars(out.raw), Basis.LAGRANGE)
+
+    def coset_extended_lagrange_to_coeffs(self, offset, ctx=None):
+        """poly.py:169-177."""
+        assert self.basis == Basis.LAGRANGE
+        n = len(self.values)
+        raw = scalars_to_bytes(self.values)
+        out = ctypes.create_string_buffer(len(raw))
+        off = (int(offset) % CURVE_ORDER).to_bytes(32, "little")
+        _lib.check(_lib.lib().pb200_fr_coset_to_coeffs_host(self._ctx(ctx).handle, raw, out, _log2_exact(n), off))
+        return Polynomial(bytes_to_scalars(out.raw), Basis.MONOMIAL)
+
+    def barycentric_eval(self, x, ctx=None):
+        """poly.py:181-195."""
+        assert self.basis == Basis.LAGRANGE
+        n = len(self.values)
+        raw = scalars_to_bytes(self.values)
+        out = ctypes.create_string_buffer(32)
+        xb = (int(x) % CURVE_ORDER).to_bytes(32, "little")
+        _lib.check(_lib.lib().pb200_fr_barycentric_eval_host(self._ctx(ctx).handle, raw, _log2_exact(n), xb, out))
+        return Scalar(int.from_bytes(out.raw, "little"))

@@ -1,0 +1,96 @@
+"""Drop-in for the reference's ``setup.py``: ``Setup`` with ``from_file`` (setup.py:24-63),
+``commit`` (setup.py:66-72) and ``verification_key`` (setup.py:75-77).  The SRS lives in HBM
+(Montgomery form -- the same encoding the .ptau file uses on disk) together with the fixed-base
+window table used by the MSM."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+from . import _lib
+from .curve import Scalar, _pt_bytes, _pt_from
+from .field import FIELD_MODULUS, FQ
+from .poly import Basis, Polynomial, _log2_exact, scalars_to_bytes
+
+SETUP_FILE_G1_STARTPOS = 80  # setup.py:11
+SETUP_FILE_POWERS_POS = 60  # setup.py:12
+_G2_GEN_X_C0 = 10857046999023057135944570762232829481370756359578518086990519993285655852781
+
+
+@dataclass
+class VerificationKey:
+    """verifier.py:10-37 (fields only; verification itself is out of this library's scope)."""
+    group_order: int
+    Qm: object
+    Ql: object
+    Qr: object
+    Qo: object
+    Qc: object
+    S1: object
+    S2: object
+    S3: object
+    X_2: object
+    w: Scalar
+
+
+class Setup:
+    def __init__(self, powers_of_x, X2, ctx: Optional[_lib.Context] = None, precompute: bool = True):
+        self.powers_of_x = powers_of_x
+        self.X2 = X2
+        self.ctx = ctx or _lib.default_context()
+        raw = b"".join(_pt_bytes(p) for p in powers_of_x)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().pb200_srs_create(self.ctx.handle, raw, len(powers_of_x), 1 if precompute else 0,
+                                               ctypes.byref(h)))
+        self._srs = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_srs", None):
+                _lib.lib().pb200_srs_destroy(self._srs)
+                self._srs = None
+        except Exception:
+            pass
+
+    @classmethod
+    def from_file(cls, filename, ctx=None, precompute=True):
+        """setup.py:24-63 -- snarkjs .ptau: byte 60 = log2(#powers), G1 points from byte 80 as
+        32-byte little-endian coordinates scaled by a constant recovered from the first point."""
+        contents = open(filename, "rb").read()
+        powers = 2 ** contents[SETUP_FILE_POWERS_POS]
+        end = SETUP_FILE_G1_STARTPOS + 64 * powers
+        values = [int.from_bytes(contents[i:i + 32], "little")
+                  for i in range(SETUP_FILE_G1_STARTPOS, end, 32)]
+        assert max(values) < FIELD_MODULUS
+        factor = values[0] % FIELD_MODULUS  # first point is the generator, x == 1
+        finv = pow(factor, -1, FIELD_MODULUS)
+        values = [v * finv % FIELD_MODULUS for v in values]
+        powers_of_x = [(FQ(values[2 * i]), FQ(values[2 * i + 1])) for i in range(powers)]
+        target = (factor * _G2_GEN_X_C0 % FIELD_MODULUS).to_bytes(32, "little")
+        pos = contents.find(target, end)
+        assert pos >= 0, "G2 section not found"
+        enc = contents[pos + 128: pos + 256]
+        xv = [int.from_bytes(enc[i:i + 32], "little") * finv % FIELD_MODULUS for i in range(0, 128, 32)]
+        X2 = ((xv[0], xv[1]), (xv[2], xv[3]))
+        return cls(powers_of_x, X2, ctx=ctx, precompute=precompute)
+
+    def commit(self, values: Polynomial):
+        """setup.py:66-72."""
+        assert values.basis == Basis.LAGRANGE
+        n = len(values.values)
+        if n > len(self.powers_of_x):
+            raise Exception("Not enough powers in setup")
+        raw = scalars_to_bytes(values.values)
+        out = ctypes.create_string_buffer(64)
+        ident = ctypes.c_int(0)
+        _lib.check(_lib.lib().pb200_srs_commit_lagrange_host(
+            self.ctx.handle, self._srs, raw, _log2_exact(n), out, ctypes.byref(ident)))
+        return _pt_from(out.raw, ident.value)
+
+    def verification_key(self, pk) -> VerificationKey:
+        """setup.py:75-77."""
+        return VerificationKey(
+            pk.group_order, self.commit(pk.QM), self.commit(pk.QL), self.commit(pk.QR), self.commit(pk.QO),
+            self.commit(pk.QC), self.commit(pk.S1), self.commit(pk.S2), self.commit(pk.S3), self.X2,
+            Scalar.root_of_unity(pk.group_order))

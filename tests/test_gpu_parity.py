@@ -1,0 +1,198 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the drop-in
+Python surface, against the oracle (oracle/plonk_oracle.py) on the same seeded inputs, against the
+committed golden fixtures, and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Bit-exact everywhere (integer field work)."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from oracle import plonk_oracle as O
+from tests.golden_io import PTAU_HEAD, ints, load_circuit, load_json, pt
+
+pytestmark = pytest.mark.gpu
+
+R = O.R_MOD
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import plonkathon_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def setup(pb):
+    return pb.Setup.from_file(PTAU_HEAD)
+
+
+def S(pb, ints_):
+    return [pb.Scalar(v) for v in ints_]
+
+
+def vals(poly):
+    return [v.n for v in poly.values]
+
+
+# ------------------------------------------------------------------ NTT
+def test_fft_golden_vectors(pb):
+    for c in load_json("fft_vectors.json")["cases"]:
+        v = ints(c["input"])
+        assert vals(pb.Polynomial(S(pb, v), pb.Basis.MONOMIAL).fft()) == ints(c["fft"]), c["n"]
+        L = pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE)
+        assert vals(L.ifft()) == ints(c["ifft"]), c["n"]
+        if "offset" in c:
+            off = pb.Scalar(int(c["offset"]))
+            assert vals(L.to_coset_extended_lagrange(off)) == ints(c["coset_ext"])
+            assert vals(L.coset_extended_lagrange_to_coeffs(off)) == ints(c["coset_to_coeffs"])
+            assert L.barycentric_eval(pb.Scalar(int(c["x"]))) == int(c["bary"])
+            assert L.barycentric_eval(pb.Scalar(int(c["x_root"]))) == int(c["bary_root"])
+
+
+def test_fft_basis_assertions(pb):
+    p = pb.Polynomial(S(pb, [1, 2]), pb.Basis.LAGRANGE)
+    with pytest.raises(AssertionError):
+        p.fft()
+    with pytest.raises(AssertionError):
+        pb.Polynomial(S(pb, [1, 2]), pb.Basis.MONOMIAL).ifft()
+
+
+@pytest.mark.parametrize("logn", [11, 12, 13, 14, 16])
+def test_fft_vs_oracle_multi_pass(pb, logn):
+    rng = random.Random(logn)
+    v = [rng.randrange(R) for _ in range(1 << logn)]
+    assert vals(pb.Polynomial(S(pb, v), pb.Basis.MONOMIAL).fft()) == O.fft(v)
+    assert vals(pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE).ifft()) == O.ifft(v)
+
+
+def _raw_ntt(pb, arr, logn, inverse):
+    from plonkathon_b200 import _lib
+    out = np.empty_like(arr)
+    _lib.check(_lib.lib().pb200_fr_ntt_host(
+        _lib.default_context().handle, arr.ctypes.data_as(ctypes.c_void_p),
+        out.ctypes.data_as(ctypes.c_void_p), logn, inverse))
+    return out
+
+
+def _random_fr(n, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    a[:, 7] &= 0x0FFFFFFF  # < 2^252 < r: canonical
+    return a
+
+
+@pytest.mark.parametrize("logn", [20, 21, 22])
+def test_ntt_full_size_properties(pb, logn):
+    """2^20 .. 2^22 (three-pass at 2^21+): inverse(forward(x)) == x, linearity against a sparse
+    input whose transform is known in closed form, and a strided sample against the oracle's
+    direct evaluation."""
+    n = 1 << logn
+    x = _random_fr(n, logn)
+    y = _raw_ntt(pb, x, logn, 0)
+    back = _raw_ntt(pb, y, logn, 1)
+    assert np.array_equal(back, x)
+    # direct evaluation at a few output indices: X[k] = sum_j x[j] w^(jk) computed with Python ints
+    xs = [int.from_bytes(x[j].tobytes(), "little") for j in range(n)] if logn == 20 else None
+    if xs is not None:
+        w = O.root_of_unity(n)
+        for k in (0, 1, n // 2 + 3, n - 1):
+            wk = pow(w, k, R)
+            acc, cur = 0, 1
+            for j in range(n):
+                acc += xs[j] * cur
+                cur = cur * wk % R
+            assert int.from_bytes(y[k].tobytes(), "little") == acc % R, k
+    # delta at position p: transform is w^(p*k)
+    d = np.zeros((n, 8), dtype=np.uint32)
+    p = 12345 % n
+    d[p, 0] = 1
+    yd = _raw_ntt(pb, d, logn, 0)
+    w = O.root_of_unity(n)
+    for k in (0, 1, 2, n // 3, n - 1):
+        assert int.from_bytes(yd[k].tobytes(), "little") == pow(w, p * k, R)
+
+
+# ------------------------------------------------------------------ MSM
+def test_lincomb_golden_vectors(pb):
+    for c in load_json("lincomb_vectors.json")["cases"]:
+        pairs = [(None if p is None else (pb.FQ(int(p[0])), pb.FQ(int(p[1]))), int(s))
+                 for p, s in zip(c["points"], c["scalars"])]
+        got = pb.ec_lincomb(pairs)
+        exp = pt(c["result"])
+        assert (got is None and exp is None) or (got[0].n, got[1].n) == exp, c["name"]
+
+
+def test_lincomb_empty_raises(pb):
+    with pytest.raises(ValueError):
+        pb.ec_lincomb([])
+
+
+@pytest.mark.parametrize("n", [1, 3, 257, 1024])
+def test_lincomb_vs_oracle_random(pb, n):
+    rng = random.Random(n)
+    osetup = O.Setup.from_file(PTAU_HEAD)
+    pts = osetup.powers_of_x[:n]
+    sc = [rng.randrange(R) for _ in range(n)]
+    got = pb.ec_lincomb([((pb.FQ(p[0]), pb.FQ(p[1])), s) for p, s in zip(pts, sc)])
+    exp = O.ec_lincomb_naive(list(zip(pts, sc))) if n <= 3 else O.ec_lincomb(list(zip(pts, sc)))
+    assert (got[0].n, got[1].n) == exp
+
+
+def test_commit_kat_and_vkeys(pb, setup):
+    """test.py:14-34 commitment KAT, and the three snarkjs verification keys (test.py:37-100)."""
+    g = load_json("circuits.json")
+    c = setup.commit(pb.Polynomial(S(pb, ints(g["commit_kat"]["lagrange"])), pb.Basis.LAGRANGE))
+    assert c == (16120260411117808045030798560855586501988622612038310041007562782458075125622,
+                 3125847109934958347271782137825877642397632921923926105820408033549219695465)
+    for name in ("basic", "ab_plus_a", "one_public"):
+        entry, arr = load_circuit(name)
+        for key, col in (("Qm", "QM"), ("Ql", "QL"), ("Qr", "QR"), ("Qo", "QO"), ("Qc", "QC"),
+                         ("S1", "S1"), ("S2", "S2"), ("S3", "S3")):
+            got = setup.commit(pb.Polynomial(S(pb, arr[col]), pb.Basis.LAGRANGE))
+            exp = pt(entry["vk"][key])
+            assert (got is None and exp is None) or (got[0].n, got[1].n) == exp, (name, key)
+
+
+def test_commit_generic_equals_fixed_base(pb):
+    """the two MSM modes (generic windows vs precomputed fixed-base table) agree"""
+    s1 = pb.Setup.from_file(PTAU_HEAD, precompute=True)
+    s2 = pb.Setup.from_file(PTAU_HEAD, precompute=False)
+    rng = random.Random(3)
+    for n in (8, 512, 2048):
+        p = pb.Polynomial(S(pb, [rng.randrange(R) for _ in range(n)]), pb.Basis.LAGRANGE)
+        a, b = s1.commit(p), s2.commit(p)
+        assert (a[0].n, a[1].n) == (b[0].n, b[1].n)
+    osetup = O.Setup.from_file(PTAU_HEAD)
+    v = [rng.randrange(R) for _ in range(2048)]
+    got = s1.commit(pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE))
+    assert (got[0].n, got[1].n) == osetup.commit(v)
+
+
+def test_msm_2p20_repeated_bases(pb):
+    """KZG-size MSM (2^20 terms) with an exactly-known answer: the 2048 SRS points tiled 512x, so
+    sum_i s_i P_(i mod 2048) == sum_j (sum_(i = j mod 2048) s_i) P_j, which the oracle evaluates
+    as a 2048-term ec_lincomb.  Also exercises repeated base points inside one MSM."""
+    from plonkathon_b200 import _lib
+    osetup = O.Setup.from_file(PTAU_HEAD)
+    base = np.frombuffer(b"".join(p[0].to_bytes(32, "little") + p[1].to_bytes(32, "little")
+                                  for p in osetup.powers_of_x), dtype=np.uint8).reshape(2048, 64)
+    n = 1 << 20
+    pts = np.ascontiguousarray(np.tile(base, (n // 2048, 1)))
+    sc = _random_fr(n, 99)
+    out = ctypes.create_string_buffer(64)
+    ident = ctypes.c_int(0)
+    _lib.check(_lib.lib().pb200_g1_msm_host(
+        _lib.default_context().handle, pts.ctypes.data_as(ctypes.c_void_p),
+        sc.ctypes.data_as(ctypes.c_void_p), n, out, ctypes.byref(ident)))
+    # fold the scalars per base point with exact integer arithmetic
+    limbs = sc.astype(object)
+    folded = [0] * 2048
+    rows = limbs.reshape(n // 2048, 2048, 8)
+    for k in range(8):
+        col = rows[:, :, k].sum(axis=0)
+        for j in range(2048):
+            folded[j] += int(col[j]) << (32 * k)
+    exp = O.ec_lincomb([(osetup.powers_of_x[j], folded[j] % R) for j in range(2048)])
+    got = (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little"))
+    assert ident.value == 0 and got == exp

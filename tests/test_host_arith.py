@@ -1,0 +1,123 @@
+"""CPU: the limb-level field / curve arithmetic of csrc/field.cuh + csrc/curve.cuh, compiled for
+the host (PTX carry primitives replaced by their emulation) and checked against Python ints and
+the oracle's affine group law.  This is the same C++ the CUDA kernels instantiate."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import plonk_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "plonkathon_b200", "csrc")
+R256 = 1 << 256
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out = os.path.join(ROOT, "build", "host_selftest.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(CSRC, "host_selftest.cpp")
+    deps = [src, os.path.join(CSRC, "field.cuh"), os.path.join(CSRC, "curve.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
+                               "-I", CSRC, "-o", out])
+    return ctypes.CDLL(out)
+
+
+def limbs(x, n=1):
+    return (ctypes.c_uint32 * (8 * n))(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(8 * n)])
+
+
+def unlimbs(buf, k=0):
+    return sum(int(buf[8 * k + i]) << (32 * i) for i in range(8))
+
+
+def fop(lib, field, op, a, b=0):
+    out = (ctypes.c_uint32 * 8)()
+    assert lib.hs_field_op(field, op, limbs(a), limbs(b), out) == 0
+    return unlimbs(out)
+
+
+EDGE = [0, 1, 2, 3, 0xFFFFFFFF, 1 << 32, (1 << 64) - 1, (1 << 128) + 1, (1 << 224) - 1]
+
+
+@pytest.mark.parametrize("field,p", [(0, O.R_MOD), (1, O.Q_MOD)])
+def test_field_ops(lib, field, p):
+    rng = random.Random(field)
+    vals = EDGE + [p - 1, p - 2, (p - 1) // 2, R256 % p, (R256 * R256) % p] + \
+        [rng.randrange(p) for _ in range(200)]
+    rinv = pow(R256, -1, p)
+    for i, a in enumerate(vals):
+        b = vals[(i * 7 + 3) % len(vals)]
+        assert fop(lib, field, 0, a, b) == (a + b) % p
+        assert fop(lib, field, 1, a, b) == (a - b) % p
+        assert fop(lib, field, 2, a, b) == a * b * rinv % p
+        assert fop(lib, field, 8, a) == a * a * rinv % p
+        assert fop(lib, field, 3, a) == (-a) % p
+        assert fop(lib, field, 7, a) == 2 * a % p
+        assert fop(lib, field, 5, a) == a * R256 % p
+        assert fop(lib, field, 6, a) == a * rinv % p
+    for a in vals[:40]:
+        am = a * R256 % p
+        inv = fop(lib, field, 4, am)
+        assert inv == (pow(a, -1, p) * R256 % p if a else 0)
+
+
+def mont(x):
+    return x * R256 % O.Q_MOD
+
+
+def unmont(x):
+    return x * pow(R256, -1, O.Q_MOD) % O.Q_MOD
+
+
+def xyzz(lib, pt):
+    """affine int point (or None) -> XYZZ limbs buffer"""
+    if pt is None:
+        return limbs(0, 4)
+    v = mont(pt[0]) | (mont(pt[1]) << 256) | (mont(1) << 512) | (mont(1) << 768)
+    return limbs(v, 4)
+
+
+def to_affine(lib, acc):
+    out = (ctypes.c_uint32 * 32)()
+    inf = lib.hs_curve_op(3, acc, limbs(0, 4), 0, out)
+    return None if inf else (unmont(unlimbs(out, 0)), unmont(unlimbs(out, 1)))
+
+
+def test_curve_ops(lib):
+    rng = random.Random(5)
+    G = O.G1
+    pts = [O.g1_multiply(G, rng.randrange(1, O.R_MOD)) for _ in range(12)]
+    for i, p in enumerate(pts):
+        q = pts[(i + 1) % len(pts)]
+        for a, b in ((p, q), (p, p), (p, O.g1_neg(p)), (None, q), (p, None)):
+            acc = xyzz(lib, a)
+            out = (ctypes.c_uint32 * 32)()
+            if b is not None:  # mixed add
+                bb = limbs(mont(b[0]) | (mont(b[1]) << 256), 2)
+                lib.hs_curve_op(0, acc, bb, 0, out)
+                assert to_affine(lib, out) == O.g1_add(a, b)
+            lib.hs_curve_op(1, acc, xyzz(lib, b), 0, out)  # full add
+            assert to_affine(lib, out) == O.g1_add(a, b)
+        # chains with non-trivial ZZ: ((p+q)+q)+(p+q) etc.
+        acc = xyzz(lib, p)
+        bb = limbs(mont(q[0]) | (mont(q[1]) << 256), 2)
+        o1 = (ctypes.c_uint32 * 32)()
+        lib.hs_curve_op(0, acc, bb, 0, o1)
+        o2 = (ctypes.c_uint32 * 32)()
+        lib.hs_curve_op(0, o1, bb, 0, o2)
+        exp = O.g1_add(O.g1_add(p, q), q)
+        assert to_affine(lib, o2) == exp
+        o3 = (ctypes.c_uint32 * 32)()
+        lib.hs_curve_op(1, o2, o1, 0, o3)
+        assert to_affine(lib, o3) == O.g1_add(exp, O.g1_add(p, q))
+        o4 = (ctypes.c_uint32 * 32)()
+        lib.hs_curve_op(1, o3, o3, 0, o4)  # projective doubling through add
+        assert to_affine(lib, o4) == O.g1_double(O.g1_add(exp, O.g1_add(p, q)))
+        o5 = (ctypes.c_uint32 * 32)()
+        lib.hs_curve_op(2, o3, limbs(0, 4), 0, o5)
+        assert to_affine(lib, o5) == to_affine(lib, o4)
