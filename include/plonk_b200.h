@@ -91,6 +91,39 @@ int pb200_srs_commit_lagrange_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t
 int pb200_srs_commit_coeffs(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m, int coeffs_montgomery,
                             uint8_t* h_out_xy, int* is_identity);
 
+/* ---- Prover (prover.py:39-306) ---------------------------------------------------------------- */
+/* prover.py:45-49  Prover(setup, program): h_pk = 8 pointers, in the order of CommonPreprocessedInput
+ * (compiler/program.py:10-30): QM QL QR QO QC S1 S2 S3, each 2^log_n Lagrange values (canonical).
+ * Converts them to coefficients and to a cached 4n coset extension in HBM. */
+int pb200_prover_create(pb200_ctx* ctx, pb200_srs* srs, unsigned log_n, const uint8_t* const* h_pk,
+                        pb200_prover** out);
+void pb200_prover_destroy(pb200_prover* p);
+/* prover.py:51-84  prove(witness): h_A/h_B/h_C = wire values per row (prover.py:97-103), h_public = the
+ * public input values in order (prover.py:57-62; the library negates them).  Writes the canonical 768-byte
+ * proof: Proof.flatten() order (prover.py:18-35), G1 as x||y, 32-byte big-endian integers.
+ * Fails (error string starts with "AssertionError") where the reference's asserts would. */
+int pb200_prover_prove(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
+                       const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768);
+/* the individual rounds, challenges supplied by the caller's transcript; outputs little-endian */
+int pb200_prover_round1(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
+                        const uint8_t* h_public, uint64_t n_public, uint8_t* h_abc_xy /*3*64*/);   /* prover.py:86 */
+int pb200_prover_round2(pb200_prover* p, const uint8_t* beta, const uint8_t* gamma, uint8_t* h_z_xy);  /* :121 */
+int pb200_prover_round3(pb200_prover* p, const uint8_t* alpha, const uint8_t* fft_cofactor,
+                        uint8_t* h_t_xy /*3*64*/);                                                   /* :154 */
+int pb200_prover_round4(pb200_prover* p, const uint8_t* zeta, uint8_t* h_evals /*6*32*/);             /* :228 */
+int pb200_prover_round5(pb200_prover* p, const uint8_t* v, uint8_t* h_w_xy /*2*64*/);                 /* :241 */
+
+/* ---- Transcript (transcript.py:58-123; host code) ---------------------------------------------- */
+int pb200_transcript_create(const uint8_t* label, size_t label_len, pb200_transcript** out);
+void pb200_transcript_destroy(pb200_transcript* t);
+int pb200_transcript_append_message(pb200_transcript* t, const uint8_t* label, size_t label_len,
+                                    const uint8_t* msg, size_t msg_len);
+int pb200_transcript_challenge_bytes(pb200_transcript* t, const uint8_t* label, size_t label_len, uint8_t* out,
+                                     size_t n);
+/* transcript.py:69-75: challenge as a canonical little-endian Fr (never zero) */
+int pb200_transcript_get_and_append_challenge(pb200_transcript* t, const uint8_t* label, size_t label_len,
+                                              uint8_t* out_le32);
+
 /* ---- micro-benchmarks (bench.py / profiles only) --------------------------------------------- */
 /* runs `iters` dependent Montgomery products per thread over `threads` threads; returns elapsed ms */
 int pb200_bench_modmul(pb200_ctx* ctx, int field /*0 Fr, 1 Fq*/, uint64_t threads, uint32_t iters, float* ms_out);

@@ -5,3 +5,5 @@ from .curve import Scalar, ec_lincomb, ec_mul, G1Point  # noqa: F401
 from .poly import Basis, Polynomial  # noqa: F401
 from .setup import Setup, VerificationKey  # noqa: F401
 from ._lib import Context, PlonkB200Error, default_context  # noqa: F401
+from .transcript import Transcript, Message1, Message2, Message3, Message4, Message5  # noqa: F401
+from .prover import Prover, Proof  # noqa: F401

@@ -52,6 +52,19 @@ def _load():
         "pb200_srs_commit_lagrange": (I, [V, V, V, U, V, P(I)]),
         "pb200_srs_commit_lagrange_host": (I, [V, V, V, U, V, P(I)]),
         "pb200_srs_commit_coeffs": (I, [V, V, V, U64, I, V, P(I)]),
+        "pb200_prover_create": (I, [V, V, U, V, P(V)]),
+        "pb200_prover_destroy": (None, [V]),
+        "pb200_prover_prove": (I, [V, V, V, V, V, U64, V]),
+        "pb200_prover_round1": (I, [V, V, V, V, V, U64, V]),
+        "pb200_prover_round2": (I, [V, V, V, V]),
+        "pb200_prover_round3": (I, [V, V, V, V]),
+        "pb200_prover_round4": (I, [V, V, V]),
+        "pb200_prover_round5": (I, [V, V, V]),
+        "pb200_transcript_create": (I, [V, ctypes.c_size_t, P(V)]),
+        "pb200_transcript_destroy": (None, [V]),
+        "pb200_transcript_append_message": (I, [V, V, ctypes.c_size_t, V, ctypes.c_size_t]),
+        "pb200_transcript_challenge_bytes": (I, [V, V, ctypes.c_size_t, V, ctypes.c_size_t]),
+        "pb200_transcript_get_and_append_challenge": (I, [V, V, ctypes.c_size_t, V]),
         "pb200_bench_modmul": (I, [V, I, U64, U, P(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():

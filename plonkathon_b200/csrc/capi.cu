@@ -4,6 +4,8 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "prover.cuh"
+#include "transcript.cuh"
 
 namespace pb200 {
 // ntt.cu
@@ -25,7 +27,18 @@ uint64_t srs_size(Srs* s);
 uint32_t msm_default_window(uint64_t n, bool fixed_base);
 void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
              bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity);
-__global__ void k_affine_to_mont(const G1Affine* in, G1Affine* out, uint64_t n);
+void affine_to_mont(Context* ctx, const G1Affine* in, G1Affine* out, uint64_t n);
+// prover.cu
+Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk);
+void prover_destroy(Prover* p);
+void prover_prove(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
+                  uint64_t n_public, uint8_t* out768);
+void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
+                   uint64_t n_public);
+void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c);
+void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c);
+void prover_round4(Prover* P, const Fr& zeta_c);
+void prover_round5(Prover* P, const Fr& v_c);
 }  // namespace pb200
 
 using namespace pb200;
@@ -219,8 +232,7 @@ int pb200_g1_msm(pb200_ctx* ctx, const void* d_points, const void* d_scalars, ui
   PB_CHECK(n > 0, "ec_lincomb of an empty list (the reference raises ValueError, curve.py:93)");
   Context* c = C(ctx);
   DevBuf mont(n * sizeof(G1Affine));
-  k_affine_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const G1Affine*)d_points, mont.as<G1Affine>(), n);
-  c->launches++;
+  affine_to_mont(c, (const G1Affine*)d_points, mont.as<G1Affine>(), n);
   msm_run(c, mont.as<G1Affine>(), n, (const Fr*)d_scalars, false, msm_default_window(n, false), false, 0, h_out_xy,
           is_identity);
   PB_API_END
@@ -272,6 +284,83 @@ int pb200_srs_commit_coeffs(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs
                             uint8_t* h_out_xy, int* is_identity) {
   PB_API_BEGIN
   srs_msm(C(ctx), reinterpret_cast<Srs*>(srs), (const Fr*)d_coeffs, m, coeffs_montgomery != 0, h_out_xy, is_identity);
+  PB_API_END
+}
+
+int pb200_prover_create(pb200_ctx* ctx, pb200_srs* srs, unsigned log_n, const uint8_t* const* h_pk,
+                        pb200_prover** out) {
+  PB_API_BEGIN
+  *out = reinterpret_cast<pb200_prover*>(prover_create(C(ctx), reinterpret_cast<Srs*>(srs), (int)log_n, h_pk));
+  PB_API_END
+}
+void pb200_prover_destroy(pb200_prover* p) { prover_destroy(reinterpret_cast<Prover*>(p)); }
+
+int pb200_prover_prove(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
+                       const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768) {
+  PB_API_BEGIN
+  prover_prove(reinterpret_cast<Prover*>(p), h_A, h_B, h_C, h_public, n_public, h_proof768);
+  PB_API_END
+}
+int pb200_prover_round1(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
+                        const uint8_t* h_public, uint64_t n_public, uint8_t* h_abc_xy) {
+  PB_API_BEGIN
+  Prover* P = reinterpret_cast<Prover*>(p);
+  prover_round1(P, h_A, h_B, h_C, h_public, n_public);
+  memcpy(h_abc_xy, P->proof.pts[0], 3 * 64);
+  PB_API_END
+}
+int pb200_prover_round2(pb200_prover* p, const uint8_t* beta, const uint8_t* gamma, uint8_t* h_z_xy) {
+  PB_API_BEGIN
+  Prover* P = reinterpret_cast<Prover*>(p);
+  prover_round2(P, load_fr_canonical(beta), load_fr_canonical(gamma));
+  memcpy(h_z_xy, P->proof.pts[3], 64);
+  PB_API_END
+}
+int pb200_prover_round3(pb200_prover* p, const uint8_t* alpha, const uint8_t* fft_cofactor, uint8_t* h_t_xy) {
+  PB_API_BEGIN
+  Prover* P = reinterpret_cast<Prover*>(p);
+  prover_round3(P, load_fr_canonical(alpha), load_fr_canonical(fft_cofactor));
+  memcpy(h_t_xy, P->proof.pts[4], 3 * 64);
+  PB_API_END
+}
+int pb200_prover_round4(pb200_prover* p, const uint8_t* zeta, uint8_t* h_evals) {
+  PB_API_BEGIN
+  Prover* P = reinterpret_cast<Prover*>(p);
+  prover_round4(P, load_fr_canonical(zeta));
+  memcpy(h_evals, P->proof.evals[0], 6 * 32);
+  PB_API_END
+}
+int pb200_prover_round5(pb200_prover* p, const uint8_t* v, uint8_t* h_w_xy) {
+  PB_API_BEGIN
+  Prover* P = reinterpret_cast<Prover*>(p);
+  prover_round5(P, load_fr_canonical(v));
+  memcpy(h_w_xy, P->proof.pts[7], 2 * 64);
+  PB_API_END
+}
+
+int pb200_transcript_create(const uint8_t* label, size_t label_len, pb200_transcript** out) {
+  PB_API_BEGIN
+  *out = reinterpret_cast<pb200_transcript*>(new Transcript(std::string((const char*)label, label_len)));
+  PB_API_END
+}
+void pb200_transcript_destroy(pb200_transcript* t) { delete reinterpret_cast<Transcript*>(t); }
+int pb200_transcript_append_message(pb200_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg,
+                                    size_t msg_len) {
+  PB_API_BEGIN
+  reinterpret_cast<Transcript*>(t)->append_message(std::string((const char*)label, label_len), msg, msg_len);
+  PB_API_END
+}
+int pb200_transcript_challenge_bytes(pb200_transcript* t, const uint8_t* label, size_t label_len, uint8_t* out,
+                                     size_t n) {
+  PB_API_BEGIN
+  reinterpret_cast<Transcript*>(t)->challenge_bytes(std::string((const char*)label, label_len), out, n);
+  PB_API_END
+}
+int pb200_transcript_get_and_append_challenge(pb200_transcript* t, const uint8_t* label, size_t label_len,
+                                              uint8_t* out_le32) {
+  PB_API_BEGIN
+  Fr f = reinterpret_cast<Transcript*>(t)->get_and_append_challenge(std::string((const char*)label, label_len));
+  memcpy(out_le32, f.v, 32);
   PB_API_END
 }
 

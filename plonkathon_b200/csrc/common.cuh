@@ -73,6 +73,7 @@ struct Context {
   std::map<int, std::unique_ptr<NttPlan>> plans;  // key: log_n * 2 + inverse
   DevBuf scratch[8];                               // reusable temporaries
   uint64_t launches = 0;                           // kernels launched through this context
+  Context();
   ~Context();
 };
 

@@ -5,7 +5,7 @@
 // reference's bit-sliced power-set method is replaced by:
 //   1. signed-digit window slicing of every scalar (c-bit windows, digits in [-2^(c-1), 2^(c-1)]),
 //      with a global histogram of bucket loads                                  (k_msm_digits)
-//   2. exclusive scan of the histogram                                           (k_scan_u32)
+//   2. exclusive scan of the histogram                                           (k_scan_*)
 //   3. counting-sort scatter of (point index, sign) by bucket                    (k_msm_scatter)
 //   4. bucket accumulation: XYZZ accumulator += affine point (8M+2S, no inversion) (k_msm_accumulate)
 //   5. bucket reduction sum_b (b+1) * B_b by running sums over bucket groups     (k_bucket_groups)
@@ -14,6 +14,8 @@
 //      which has to read the point anyway to feed the Fiat-Shamir transcript.
 // Two modes: "generic" (arbitrary points: W windows x 2^(c-1) buckets) and "fixed-base" (SRS with the
 // window multiples 2^(c*w) * P_i precomputed in HBM: one shared set of 2^(c-1) buckets, no Horner).
+#include <cstring>
+
 #include "common.cuh"
 
 namespace pb200 {
@@ -71,30 +73,75 @@ __global__ void k_msm_histogram(const Fr* scalars, uint64_t n, int from_mont, Ms
   }
 }
 
-// single-block exclusive scan: offsets[0..nb] from counts[0..nb-1]; also zeroes counts (reused as cursors)
-__global__ void k_scan_u32(uint32_t* counts, uint32_t* offsets, uint32_t nb) {
-  __shared__ uint32_t part[1024];
-  uint32_t tid = threadIdx.x;
-  uint32_t per = (nb + 1023) / 1024;
-  uint32_t lo = tid * per, hi = min(lo + per, nb);
-  uint32_t s = 0;
-  for (uint32_t i = lo; i < hi; i++) s += counts[i];
-  part[tid] = s;
+// ---- exclusive scan of the bucket histogram (3 small kernels) ---------------------------------
+// offsets[0..nb] from counts[0..nb-1]; counts are zeroed on the way out (reused as scatter cursors)
+#define PB_SCAN_TILE 2048  // entries per block (256 threads x 8)
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* sh, uint32_t* total) {
+  // 256 threads; returns exclusive prefix of v across the block, *total = block sum
+  uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if ((int)lane >= d) x += y;
+  }
+  if (lane == 31) sh[wid] = x;
   __syncthreads();
-  for (uint32_t d = 1; d < 1024; d <<= 1) {
-    uint32_t v = tid >= d ? part[tid - d] : 0;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < 8 ? sh[lane] : 0;
+    for (int d = 1; d < 8; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+      if ((int)lane >= d) w += y;
+    }
+    if (lane < 8) sh[lane] = w;  // inclusive warp totals
   }
-  uint32_t run = tid ? part[tid - 1] : 0;
+  __syncthreads();
+  uint32_t base = wid ? sh[wid - 1] : 0;
+  *total = sh[7];
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* counts, uint32_t nb, uint32_t* tile_sums) {
+  __shared__ uint32_t sh[8];
+  uint32_t base = blockIdx.x * PB_SCAN_TILE + threadIdx.x * 8;
+  uint32_t s = 0;
+  for (int k = 0; k < 8; k++) if (base + k < nb) s += counts[base + k];
+  uint32_t total;
+  block_exclusive_scan_256(s, sh, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to 256*32 tile sums in place; writes the grand total to *total_out
+__global__ void __launch_bounds__(256) k_scan_tiles(uint32_t* tile_sums, uint32_t n_tiles, uint32_t* total_out) {
+  __shared__ uint32_t sh[8];
+  uint32_t per = (n_tiles + 255) / 256;
+  uint32_t lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += tile_sums[i];
+  uint32_t total;
+  uint32_t run = block_exclusive_scan_256(s, sh, &total);
   for (uint32_t i = lo; i < hi; i++) {
-    uint32_t c = counts[i];
-    offsets[i] = run;
+    uint32_t c = tile_sums[i];
+    tile_sums[i] = run;
     run += c;
-    counts[i] = 0;
   }
-  if (tid == 1023) offsets[nb] = part[1023];
+  if (threadIdx.x == 0) *total_out = total;
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t* counts, uint32_t nb, const uint32_t* tile_sums,
+                                                    uint32_t* offsets) {
+  __shared__ uint32_t sh[8];
+  uint32_t base = blockIdx.x * PB_SCAN_TILE + threadIdx.x * 8;
+  uint32_t c[8];
+  uint32_t s = 0;
+  for (int k = 0; k < 8; k++) { c[k] = base + k < nb ? counts[base + k] : 0; s += c[k]; }
+  uint32_t total;
+  uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan_256(s, sh, &total);
+  for (int k = 0; k < 8; k++) {
+    if (base + k < nb) { offsets[base + k] = run; counts[base + k] = 0; }
+    run += c[k];
+  }
 }
 
 // sorted[offsets[key] + cursor++] = point index | sign << 31
@@ -113,20 +160,119 @@ __global__ void k_msm_scatter(const Fr* scalars, uint64_t n, int from_mont, MsmG
   }
 }
 
-// one thread per bucket: B_b = sum of its (signed) points
-__global__ void __launch_bounds__(128) k_msm_accumulate(const G1Affine* points, const uint32_t* offsets,
-                                                        const uint32_t* sorted, uint32_t nb, G1XYZZ* buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nb) return;
-  uint32_t lo = offsets[b], hi = offsets[b + 1];
-  G1XYZZ acc = G1XYZZ::identity();
-  for (uint32_t e = lo; e < hi; e++) {
-    uint32_t v = sorted[e];
-    G1Affine p = ld_affine(points + (v & 0x7fffffffu));
-    if (v >> 31) p.y = fp_neg(p.y);
-    g1_add_mixed(acc, p);
+// ---- load-balanced bucket accumulation ------------------------------------------------------
+// The sorted entry array is cut into fixed segments of L entries, one thread each, so every thread does
+// the same number of mixed additions no matter how skewed the bucket loads are (real witnesses are full
+// of zeros / ones / small constants, and the top window of a 254-bit scalar is always lopsided).
+// A bucket that lies inside one segment is written directly.  A bucket that crosses a segment boundary
+// leaves partial sums in two slots per segment (slot 2t: the segment's first run, slot 2t+1: its last
+// run); the segment in which the bucket starts "owns" it and stitches the partials together afterwards:
+// by itself when few segments are involved, through a block-wide tree for heavy buckets.
+#define PB_MSM_EMPTY 0xffffffffu
+
+__device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t key) {
+  // first index i in [0, n) with a[i] > key (n if none)
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) > key) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128) k_msm_seg_accumulate(const G1Affine* points, const uint32_t* offsets,
+                                                            const uint32_t* sorted, uint32_t nb, uint32_t L,
+                                                            G1XYZZ* buckets, G1XYZZ* slots, uint32_t* slot_bucket,
+                                                            uint32_t* own_slot) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t M = offsets[nb];
+  const uint64_t s64 = (uint64_t)t * L;
+  if (s64 >= M) return;
+  const uint32_t s = (uint32_t)s64;
+  const uint32_t e = (uint32_t)min((uint64_t)M, s64 + L);
+  uint32_t b = upper_bound_u32(offsets, nb + 1, s) - 1;  // offsets[b] <= s < offsets[b+1]
+  uint32_t pos = s;
+  bool first = true;
+  while (pos < e) {
+    const uint32_t bstart = offsets[b], bend = offsets[b + 1];
+    const uint32_t run_end = min(bend, e);
+    G1XYZZ acc = G1XYZZ::identity();
+    for (; pos < run_end; pos++) {
+      uint32_t v = __ldg(sorted + pos);
+      G1Affine p = ld_affine(points + (v & 0x7fffffffu));
+      if (v >> 31) p.y = fp_neg(p.y);
+      g1_add_mixed(acc, p);
+    }
+    if (bstart >= s && bend <= e) {
+      buckets[b] = acc;
+    } else {
+      uint32_t slot = first ? 2 * t : 2 * t + 1;
+      slots[slot] = acc;
+      slot_bucket[slot] = b;
+      if (bstart >= s) own_slot[t] = slot;  // the bucket starts here and continues past e
+    }
+    first = false;
+    if (pos < e) {
+      b++;
+      while (offsets[b + 1] <= pos) b++;  // skip empty buckets
+    }
+  }
+}
+
+struct HeavyItem { uint32_t bucket, own_slot, t0, t1; };
+
+// one thread per segment: if it owns a boundary-crossing bucket, stitch it (or queue it as heavy)
+__global__ void __launch_bounds__(128) k_msm_stitch(const uint32_t* offsets, uint32_t nb, uint32_t L,
+                                                    uint32_t n_segments, const G1XYZZ* slots,
+                                                    const uint32_t* slot_bucket, const uint32_t* own_slot,
+                                                    G1XYZZ* buckets, HeavyItem* heavy, uint32_t* heavy_count,
+                                                    uint32_t small_limit) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_segments) return;
+  const uint32_t os = own_slot[t];
+  if (os == PB_MSM_EMPTY) return;
+  const uint32_t b = slot_bucket[os];
+  const uint32_t t1 = (offsets[b + 1] - 1) / L;  // last segment the bucket reaches
+  if (t1 - t > small_limit) {
+    uint32_t h = atomicAdd(heavy_count, 1u);
+    HeavyItem it; it.bucket = b; it.own_slot = os; it.t0 = t; it.t1 = t1;
+    heavy[h] = it;
+    return;
+  }
+  G1XYZZ acc = slots[os];
+  for (uint32_t k = t + 1; k <= t1; k++) {
+    G1XYZZ piece = slots[2 * k];
+    g1_add(acc, piece);
   }
   buckets[b] = acc;
+}
+
+// heavy buckets: one block each (grid-stride over the queue), strided partial sums + shared-memory tree
+__global__ void __launch_bounds__(128) k_msm_stitch_heavy(const G1XYZZ* slots, const HeavyItem* heavy,
+                                                          const uint32_t* heavy_count, G1XYZZ* buckets) {
+  __shared__ G1XYZZ sh[128];
+  const uint32_t count = *heavy_count;
+  for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+    HeavyItem it = heavy[h];
+    G1XYZZ acc = G1XYZZ::identity();
+    if (threadIdx.x == 0) acc = slots[it.own_slot];
+    for (uint32_t k = it.t0 + 1 + threadIdx.x; k <= it.t1; k += blockDim.x) {
+      G1XYZZ piece = slots[2 * k];
+      g1_add(acc, piece);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+      if (threadIdx.x < d) {
+        G1XYZZ a = sh[threadIdx.x], c = sh[threadIdx.x + d];
+        g1_add(a, c);
+        sh[threadIdx.x] = a;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[it.bucket] = sh[0];
+    __syncthreads();
+  }
 }
 
 // acc = k * p (k < 2^31), double-and-add from the top bit
@@ -202,6 +348,12 @@ __global__ void __launch_bounds__(128) k_window_step(const G1Affine* in, G1XYZZ*
   g1_double_affine(a, p);
   for (uint32_t k = 1; k < c; k++) g1_double(a);
   out[i] = a;
+}
+
+void affine_to_mont(Context* ctx, const G1Affine* in, G1Affine* out, uint64_t n) {
+  k_affine_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(in, out, n);
+  ctx->launches++;
+  PB_CUDA(cudaGetLastError());
 }
 
 // XYZZ -> affine with Montgomery's batch-inversion trick, CH points per thread (none is the identity)
@@ -288,7 +440,12 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   DevBuf& buckets = ctx->scratch[5];
   DevBuf& groups = ctx->scratch[6];
   DevBuf& wsums = ctx->scratch[7];
+  DevBuf& seg = ctx->scratch[1];
+  uint32_t seg_len = 32;
+  if (const char* e = getenv("PB200_MSM_SEG")) seg_len = (uint32_t)atoi(e);
+  PB_CHECK(seg_len >= 1 && seg_len <= 4096, "bad PB200_MSM_SEG");
   uint64_t entries = n * g.W;
+  PB_CHECK(entries < (1ull << 32), "MSM too large (n * windows must fit 32 bits)");
   sorted.ensure(entries * 4);
   counts.ensure((size_t)g.nb * 4);
   offsets.ensure((size_t)(g.nb + 1) * 4);
@@ -296,17 +453,43 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   uint32_t gsz = g.half >= 64 ? 64 : g.half;
   uint32_t n_groups = g.nb / gsz;
   groups.ensure((size_t)n_groups * sizeof(G1XYZZ));
-  wsums.ensure((size_t)n_windows_out * sizeof(G1XYZZ));
+  wsums.ensure((size_t)n_windows_out * sizeof(G1XYZZ) + 8192 * 4);
 
   cudaStream_t st = ctx->stream;
   PB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)g.nb * 4, st));
   unsigned blocks = (unsigned)((n + 127) / 128);
   k_msm_histogram<<<blocks, 128, 0, st>>>(scalars, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
-  k_scan_u32<<<1, 1024, 0, st>>>(counts.as<uint32_t>(), offsets.as<uint32_t>(), g.nb);
+  {
+    uint32_t n_tiles = (g.nb + PB_SCAN_TILE - 1) / PB_SCAN_TILE;
+    PB_CHECK(n_tiles <= 8192, "too many buckets for the scan");
+    uint32_t* tile_sums = reinterpret_cast<uint32_t*>(wsums.as<unsigned char>() + (size_t)n_windows_out * sizeof(G1XYZZ));
+    k_scan_tile_sums<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums);
+    k_scan_tiles<<<1, 256, 0, st>>>(tile_sums, n_tiles, offsets.as<uint32_t>() + g.nb);
+    k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums, offsets.as<uint32_t>());
+    ctx->launches += 2;
+  }
   k_msm_scatter<<<blocks, 128, 0, st>>>(scalars, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
                                         counts.as<uint32_t>(), sorted.as<uint32_t>());
-  k_msm_accumulate<<<(g.nb + 127) / 128, 128, 0, st>>>(points, offsets.as<uint32_t>(), sorted.as<uint32_t>(), g.nb,
-                                                      buckets.as<G1XYZZ>());
+  // balanced accumulation over fixed segments of L sorted entries
+  {
+    const uint32_t L = seg_len;
+    const uint32_t n_seg = (uint32_t)((entries + L - 1) / L);
+    seg.ensure((size_t)n_seg * 2 * sizeof(G1XYZZ) + (size_t)n_seg * 3 * 4 + (size_t)n_seg * sizeof(HeavyItem) + 16);
+    G1XYZZ* slots = seg.as<G1XYZZ>();
+    uint32_t* slot_bucket = reinterpret_cast<uint32_t*>(slots + (size_t)n_seg * 2);
+    uint32_t* own_slot = slot_bucket + (size_t)n_seg * 2;
+    uint32_t* heavy_count = own_slot + n_seg;
+    HeavyItem* heavy = reinterpret_cast<HeavyItem*>(heavy_count + 4);
+    PB_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)g.nb * sizeof(G1XYZZ), st));
+    PB_CUDA(cudaMemsetAsync(own_slot, 0xff, (size_t)n_seg * 4, st));
+    PB_CUDA(cudaMemsetAsync(heavy_count, 0, 16, st));
+    k_msm_seg_accumulate<<<(n_seg + 127) / 128, 128, 0, st>>>(points, offsets.as<uint32_t>(), sorted.as<uint32_t>(),
+                                                             g.nb, L, buckets.as<G1XYZZ>(), slots, slot_bucket, own_slot);
+    k_msm_stitch<<<(n_seg + 127) / 128, 128, 0, st>>>(offsets.as<uint32_t>(), g.nb, L, n_seg, slots, slot_bucket,
+                                                     own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, 16);
+    k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, buckets.as<G1XYZZ>());
+    ctx->launches += 2;
+  }
   k_bucket_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(buckets.as<G1XYZZ>(), g.half, gsz, n_groups,
                                                          groups.as<G1XYZZ>());
   k_sum_points<<<n_windows_out, 128, 0, st>>>(groups.as<G1XYZZ>(), g.half / gsz, wsums.as<G1XYZZ>());

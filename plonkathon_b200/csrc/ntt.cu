@@ -378,6 +378,8 @@ NttPlan* get_plan(Context* ctx, int log_n, bool inverse) {
   return raw;
 }
 
+Context::Context() {}
+
 Context::~Context() {
   plans.clear();
   if (own_stream && stream) cudaStreamDestroy(stream);

@@ -1,0 +1,593 @@
+// Device-resident PLONK prover: rounds 1-5 of prover.py:51-306 (`Prover.prove`, `round_1..5`).
+//
+// The reference's round bodies are stubs in the mounted branch; the computation follows the in-tree
+// comments, the sanity asserts and the completed test verifier (see SURVEY App. D and
+// oracle/plonk_oracle.py, which is pinned by test/proof.pickle).  Every output (9 G1 points, 6 scalars) is
+// mathematically unique -- the reference prover has no blinding -- so the work is restructured freely:
+//   * all vectors stay in HBM in Montgomery form; only the 15 proof values cross to the host, once per round,
+//     because the Merlin transcript is host code;
+//   * selector / permutation polynomials are converted to coefficients and coset-extended once per circuit
+//     (Prover creation), on a FIXED coset g*<w_4n> (g = 5): the quotient T(X) does not depend on which coset
+//     it is interpolated from, so the transcript's `fft_cofactor` challenge is drawn (it is part of the
+//     transcript schedule, transcript.py:88-97) but not needed for the arithmetic;
+//   * T1, T2, T3, R, W_z, W_zw are committed from their coefficients directly (the reference's
+//     fft -> commit -> ifft round trip is the identity, setup.py:66-72);
+//   * round 4 evaluates coefficient forms by parallel Horner instead of barycentric sums (same values);
+//   * round 5 builds R(X) and the opening numerators in coefficient form; the divisions by (X - zeta) and
+//     (X - zeta*w) are done on an n-point coset (quotient degree n-2 < n).
+// The reference's run-time invariants are kept as checks that fail the call: gate satisfaction
+// (prover.py:108-116), Z_n == 1 (prover.py:132), deg T < 3n (prover.py:205-208).
+#include "common.cuh"
+#include "transcript.cuh"
+#include "prover.cuh"
+
+namespace pb200 {
+
+void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in, const Fr* in_scale,
+             const Fr* out_scale);
+void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
+Fr fr_from_u64(uint64_t x);
+Fr fr_root_of_unity(int log_n);
+void fr_to_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
+struct Srs;
+void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
+uint64_t srs_size(Srs* s);
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+#define PB_GRID(n, t) (unsigned)(((n) + (t)-1) / (t)), (t)
+
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// prover.py:108-116: A*QL + B*QR + A*B*QM + C*QO + PI + QC == 0 on every row
+__global__ void k_gate_check(const Fr* A, const Fr* B, const Fr* C, const Fr* QL, const Fr* QR, const Fr* QM,
+                             const Fr* QO, const Fr* QC, const Fr* PI, uint64_t n, uint32_t* bad) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr a = ldg_fr(A + i), b = ldg_fr(B + i), c = ldg_fr(C + i);
+  Fr s = fp_mul(a, ldg_fr(QL + i));
+  s = fp_add(s, fp_mul(b, ldg_fr(QR + i)));
+  s = fp_add(s, fp_mul(fp_mul(a, b), ldg_fr(QM + i)));
+  s = fp_add(s, fp_mul(c, ldg_fr(QO + i)));
+  s = fp_add(s, fp_add(ldg_fr(PI + i), ldg_fr(QC + i)));
+  if (!s.is_zero()) atomicAdd(bad, 1u);
+}
+
+// prover.py:125-131: per-row numerator / denominator of the grand product
+struct PermChallenges { Fr beta, gamma; };
+__global__ void k_perm_terms(const Fr* A, const Fr* B, const Fr* C, const Fr* S1, const Fr* S2, const Fr* S3,
+                             const Fr* roots, PermChallenges ch, uint64_t n, Fr* num, Fr* den) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr a = fp_add(ldg_fr(A + i), ch.gamma), b = fp_add(ldg_fr(B + i), ch.gamma), c = fp_add(ldg_fr(C + i), ch.gamma);
+  Fr bw = fp_mul(ch.beta, ldg_fr(roots + i));
+  Fr bw2 = fp_dbl(bw), bw3 = fp_add(bw2, bw);
+  num[i] = fp_mul(fp_mul(fp_add(a, bw), fp_add(b, bw2)), fp_add(c, bw3));
+  Fr d1 = fp_add(a, fp_mul(ch.beta, ldg_fr(S1 + i)));
+  Fr d2 = fp_add(b, fp_mul(ch.beta, ldg_fr(S2 + i)));
+  Fr d3 = fp_add(c, fp_mul(ch.beta, ldg_fr(S3 + i)));
+  den[i] = fp_mul(fp_mul(d1, d2), d3);
+}
+
+// out[i] = num[i] / den[i] (inv(0) = 0), Montgomery's trick over the strided set {t, t+T, ...}
+// (strided so the accesses of a warp are coalesced).  num may be null (plain inversion).
+__global__ void __launch_bounds__(128) k_batch_div(const Fr* num, const Fr* den, Fr* out, uint64_t n, uint64_t T) {
+  const int CH = 8;
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fr pref[CH];
+  Fr run = Fr::one();
+  int cnt = 0;
+  for (int k = 0; k < CH; k++) {
+    uint64_t i = t + (uint64_t)k * T;
+    if (i >= n) break;
+    Fr d = ldg_fr(den + i);
+    if (d.is_zero()) d = Fr::one();
+    pref[k] = run;
+    run = fp_mul(run, d);
+    cnt++;
+  }
+  Fr inv = fp_inv(run);
+  for (int k = cnt - 1; k >= 0; k--) {
+    uint64_t i = t + (uint64_t)k * T;
+    Fr d = ldg_fr(den + i);
+    bool z = d.is_zero();
+    if (z) d = Fr::one();
+    Fr ik = fp_mul(inv, pref[k]);
+    inv = fp_mul(inv, d);
+    Fr r = z ? Fr::zero() : ik;
+    if (num) r = fp_mul(r, ldg_fr(num + i));
+    out[i] = r;
+  }
+}
+
+// ---- exclusive prefix product: Z[0] = 1, Z[i+1] = Z[i] * f[i]   (3 kernels, tiles of 256 x 8) ----
+#define PB_PROD_TILE 2048
+__device__ __forceinline__ Fr block_exclusive_prod_256(const Fr& v, Fr* sh, Fr* total) {
+  // Hillis-Steele over 256 threads in shared memory (inclusive), then shift
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    Fr x = sh[threadIdx.x];
+    Fr y = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : Fr::one();
+    __syncthreads();
+    if ((int)threadIdx.x >= d) sh[threadIdx.x] = fp_mul(x, y);
+    __syncthreads();
+  }
+  Fr excl = threadIdx.x ? sh[threadIdx.x - 1] : Fr::one();
+  *total = sh[255];
+  __syncthreads();
+  return excl;
+}
+__global__ void __launch_bounds__(256) k_prod_tiles(const Fr* f, uint64_t n, Fr* tile_prod) {
+  __shared__ Fr sh[256];
+  uint64_t base = (uint64_t)blockIdx.x * PB_PROD_TILE + threadIdx.x * 8;
+  Fr p = Fr::one();
+  for (int k = 0; k < 8; k++) if (base + k < n) p = fp_mul(p, ldg_fr(f + base + k));
+  Fr total;
+  block_exclusive_prod_256(p, sh, &total);
+  if (threadIdx.x == 0) tile_prod[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_prod_scan_tiles(Fr* tile_prod, uint32_t n_tiles, Fr* total_out) {
+  __shared__ Fr sh[256];
+  uint32_t per = (n_tiles + 255) / 256;
+  uint32_t lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
+  Fr p = Fr::one();
+  for (uint32_t i = lo; i < hi; i++) p = fp_mul(p, tile_prod[i]);
+  Fr total;
+  Fr run = block_exclusive_prod_256(p, sh, &total);
+  for (uint32_t i = lo; i < hi; i++) {
+    Fr c = tile_prod[i];
+    tile_prod[i] = run;
+    run = fp_mul(run, c);
+  }
+  if (threadIdx.x == 0) *total_out = total;
+}
+__global__ void __launch_bounds__(256) k_prod_apply(const Fr* f, uint64_t n, const Fr* tile_prod, Fr* Z) {
+  __shared__ Fr sh[256];
+  uint64_t base = (uint64_t)blockIdx.x * PB_PROD_TILE + threadIdx.x * 8;
+  Fr c[8];
+  Fr p = Fr::one();
+  for (int k = 0; k < 8; k++) { c[k] = base + k < n ? ldg_fr(f + base + k) : Fr::one(); p = fp_mul(p, c[k]); }
+  Fr total;
+  Fr run = fp_mul(tile_prod[blockIdx.x], block_exclusive_prod_256(p, sh, &total));
+  for (int k = 0; k < 8; k++) {
+    if (base + k < n) Z[base + k] = run;
+    run = fp_mul(run, c[k]);
+  }
+}
+
+// ---- round 3: quotient on the fixed coset -----------------------------------------------------------------
+struct QuotientArgs {
+  const Fr *A, *B, *C, *Z, *PI;                       // extended (4n)
+  const Fr *QL, *QR, *QM, *QO, *QC, *S1, *S2, *S3;    // extended, cached per circuit
+  const Fr *L0, *X;                                   // extended L0 and the coset points
+  Fr zh_inv[4];                                       // 1 / (x_j^n - 1) for j mod 4
+  Fr alpha, alpha2, beta, gamma, one;
+  uint64_t n4;
+};
+__global__ void __launch_bounds__(128) k_quotient(QuotientArgs q, Fr* T) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= q.n4) return;
+  uint64_t jw = j + 4 >= q.n4 ? j + 4 - q.n4 : j + 4;
+  Fr a = ldg_fr(q.A + j), b = ldg_fr(q.B + j), c = ldg_fr(q.C + j);
+  Fr gate = fp_mul(a, ldg_fr(q.QL + j));
+  gate = fp_add(gate, fp_mul(b, ldg_fr(q.QR + j)));
+  gate = fp_add(gate, fp_mul(fp_mul(a, b), ldg_fr(q.QM + j)));
+  gate = fp_add(gate, fp_mul(c, ldg_fr(q.QO + j)));
+  gate = fp_add(gate, fp_add(ldg_fr(q.PI + j), ldg_fr(q.QC + j)));
+  Fr ag = fp_add(a, q.gamma), bg = fp_add(b, q.gamma), cg = fp_add(c, q.gamma);
+  Fr bx = fp_mul(q.beta, ldg_fr(q.X + j));
+  Fr bx2 = fp_dbl(bx), bx3 = fp_add(bx2, bx);
+  Fr z = ldg_fr(q.Z + j), zw = ldg_fr(q.Z + jw);
+  Fr p1 = fp_mul(fp_mul(fp_mul(fp_add(ag, bx), fp_add(bg, bx2)), fp_add(cg, bx3)), z);
+  Fr p2 = fp_mul(fp_mul(fp_mul(fp_add(ag, fp_mul(q.beta, ldg_fr(q.S1 + j))), fp_add(bg, fp_mul(q.beta, ldg_fr(q.S2 + j)))),
+                        fp_add(cg, fp_mul(q.beta, ldg_fr(q.S3 + j)))),
+                 zw);
+  Fr perm = fp_mul(q.alpha, fp_sub(p1, p2));
+  Fr l0 = fp_mul(q.alpha2, fp_mul(fp_sub(z, q.one), ldg_fr(q.L0 + j)));
+  Fr num = fp_add(fp_add(gate, perm), l0);
+  T[j] = fp_mul(num, q.zh_inv[j & 3]);
+}
+
+// number of non-zero entries among v[0..n)
+__global__ void k_count_nonzero(const Fr* v, uint64_t n, uint32_t* cnt) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !ldg_fr(v + i).is_zero()) atomicAdd(cnt, 1u);
+}
+
+// ---- parallel Horner: polys[p] (n coefficients) at xs[p] ------------------------------------------------
+// level 1: H[p][c] = sum_k coeff[p][k*NC + c] * (x^NC)^k  for c < NC   (coalesced across c)
+struct EvalArgs { const Fr* poly[8]; Fr x_nc[8]; uint64_t n; uint32_t NC; };
+__global__ void __launch_bounds__(128) k_horner_strided(EvalArgs a, Fr* H) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t p = blockIdx.y;
+  if (c >= a.NC) return;
+  const Fr* co = a.poly[p];
+  uint64_t steps = a.n / a.NC;
+  Fr acc = Fr::zero();
+  for (uint64_t k = steps; k-- > 0;) acc = fp_add(fp_mul(acc, a.x_nc[p]), ldg_fr(co + k * a.NC + c));
+  H[(uint64_t)p * a.NC + c] = acc;
+}
+
+// ---- coefficient-space linear combination: out[k] = sum_i w[i] * vec[i][k] (+ c0 at k == 0) -----------------
+struct LinCombArgs { const Fr* vec[16]; Fr w[16]; Fr c0; int count; uint64_t n; };
+__global__ void __launch_bounds__(128) k_lincomb(LinCombArgs a, Fr* out) {
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.n) return;
+  Fr acc = k == 0 ? a.c0 : Fr::zero();
+  for (int i = 0; i < a.count; i++) acc = fp_add(acc, fp_mul(a.w[i], ldg_fr(a.vec[i] + k)));
+  out[k] = acc;
+}
+
+// den[j] = shift * roots[j] - point    (the n-point coset x_j = shift * w^j minus the opening point)
+__global__ void k_coset_minus(const Fr* roots, Fr shift, Fr point, uint64_t n, Fr* den) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) den[j] = fp_sub(fp_mul(shift, ldg_fr(roots + j)), point);
+}
+
+// out[j] = 1 / (n * (x_j - 1)) * (x_j^n - 1),   x_j = X[j], x_j^n = gn * i4[j & 3]
+__global__ void k_l0_num(const Fr* X, uint64_t n4, Fr n_mont, Fr one, Fr* den) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n4) den[j] = fp_mul(n_mont, fp_sub(ldg_fr(X + j), one));
+}
+struct Four { Fr v[4]; };
+__global__ void k_scale_by4(Fr* v, uint64_t n4, Four m) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n4) v[j] = fp_mul(v[j], m.v[j & 3]);
+}
+__global__ void k_negate(Fr* v, uint64_t n) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) v[j] = fp_neg(v[j]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+static void upload_mont(Context* ctx, DevBuf& dst, const uint8_t* h, uint64_t n) {
+  dst.ensure(n * 32);
+  PB_CUDA(cudaMemcpyAsync(dst.p, h, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  fr_to_mont(ctx, dst.as<Fr>(), dst.as<Fr>(), n);
+}
+
+// h_pk: 8 vectors (QM QL QR QO QC S1 S2 S3), each n x 32 bytes canonical (compiler/program.py:10-30)
+Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk) {
+  auto P = std::make_unique<Prover>();
+  P->ctx = ctx;
+  P->srs = srs;
+  P->log_n = log_n;
+  const uint64_t n = (uint64_t)1 << log_n, n4 = 4 * n;
+  P->n = n;
+  PB_CHECK(log_n >= 1 && log_n <= 26, "group order must be 2^k, 1 <= k <= 26");
+  PB_CHECK(n <= srs_size(srs), "Not enough powers in setup");
+  cudaStream_t st = ctx->stream;
+  P->g = fr_from_u64(5);
+  P->g_inv = fp_inv(P->g);
+  Fr one = Fr::one();
+  // tables
+  P->roots.alloc(n * 32);
+  launch_powers(ctx, P->roots.as<Fr>(), n, fr_root_of_unity(log_n), one);
+  P->gpow.alloc(n * 32);
+  launch_powers(ctx, P->gpow.as<Fr>(), n, P->g, one);
+  P->ginv_pow.alloc(n4 * 32);
+  launch_powers(ctx, P->ginv_pow.as<Fr>(), n4, P->g_inv, one);
+  P->xs.alloc(n4 * 32);
+  launch_powers(ctx, P->xs.as<Fr>(), n4, fr_root_of_unity(log_n + 2), P->g);
+  // Z_H on the coset takes 4 values: g^n * i^(j mod 4) - 1, i = mu^n
+  Fr gn = fp_pow_u64(P->g, n);
+  Fr i4 = fp_pow_u64(fr_root_of_unity(log_n + 2), n);
+  Four zh;
+  Fr cur = gn;
+  for (int k = 0; k < 4; k++) {
+    zh.v[k] = fp_sub(cur, one);
+    P->zh_inv[k] = fp_inv(zh.v[k]);
+    cur = fp_mul(cur, i4);
+  }
+  // L0(x_j) = (x_j^n - 1) / (n (x_j - 1))
+  P->l0_ext.alloc(n4 * 32);
+  {
+    DevBuf den(n4 * 32);
+    k_l0_num<<<PB_GRID(n4, 256), 0, st>>>(P->xs.as<Fr>(), n4, fr_from_u64(n), one, den.as<Fr>());
+    uint64_t T = (n4 + 7) / 8;
+    k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), P->l0_ext.as<Fr>(), n4, T);
+    k_scale_by4<<<PB_GRID(n4, 256), 0, st>>>(P->l0_ext.as<Fr>(), n4, zh);
+    ctx->launches += 3;
+    PB_CUDA(cudaStreamSynchronize(st));
+  }
+  for (int k = 0; k < 8; k++) {
+    upload_mont(ctx, P->sel_lag[k], h_pk[k], n);
+    P->sel_coeff[k].alloc(n * 32);
+    ntt_run(ctx, P->sel_lag[k].as<Fr>(), P->sel_coeff[k].as<Fr>(), log_n, true, n, nullptr, nullptr);
+    P->sel_ext[k].alloc(n4 * 32);
+    ntt_run(ctx, P->sel_coeff[k].as<Fr>(), P->sel_ext[k].as<Fr>(), log_n + 2, false, n, P->gpow.as<Fr>(), nullptr);
+  }
+  for (int k = 0; k < 4; k++) P->lag[k].alloc(n * 32);
+  for (int k = 0; k < 5; k++) { P->coeff[k].alloc(n * 32); P->ext[k].alloc(n4 * 32); }
+  P->pi_lag.alloc(n * 32);
+  P->tq.alloc(n4 * 32);
+  for (int k = 0; k < 4; k++) P->tmp[k].alloc(n * 32);
+  P->flags.alloc(64);
+  PB_CUDA(cudaStreamSynchronize(st));
+  PB_CUDA(cudaGetLastError());
+  return P.release();
+}
+
+void prover_destroy(Prover* p) { delete p; }
+
+static uint32_t read_flag(Prover* P, int idx) {
+  uint32_t v;
+  PB_CUDA(cudaMemcpyAsync(&v, P->flags.as<uint32_t>() + idx, 4, cudaMemcpyDeviceToHost, P->ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(P->ctx->stream));
+  return v;
+}
+
+// evaluate up to 8 coefficient-form polynomials (n coeffs each, Montgomery) at Montgomery points:
+// two strided-Horner levels on the device (n -> 4096 -> 32 partial values), the last 32 on the host
+static void eval_polys(Prover* P, int count, const Fr* const* polys, const Fr* xs, Fr* out) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n;
+  uint32_t NC1 = (uint32_t)std::min<uint64_t>(n, 4096);
+  uint32_t NC2 = std::min<uint32_t>(NC1, 32);
+  ctx->scratch[0].ensure((size_t)count * (NC1 + NC2) * 32);
+  Fr* H1 = ctx->scratch[0].as<Fr>();
+  Fr* H2 = H1 + (size_t)count * NC1;
+  EvalArgs a;
+  a.n = n;
+  a.NC = NC1;
+  for (int p = 0; p < count; p++) { a.poly[p] = polys[p]; a.x_nc[p] = fp_pow_u64(xs[p], NC1); }
+  k_horner_strided<<<dim3((NC1 + 127) / 128, count), 128, 0, ctx->stream>>>(a, H1);
+  EvalArgs b;
+  b.n = NC1;
+  b.NC = NC2;
+  for (int p = 0; p < count; p++) { b.poly[p] = H1 + (size_t)p * NC1; b.x_nc[p] = fp_pow_u64(xs[p], NC2); }
+  k_horner_strided<<<dim3((NC2 + 127) / 128, count), 128, 0, ctx->stream>>>(b, H2);
+  ctx->launches += 2;
+  std::vector<Fr> h((size_t)count * NC2);
+  PB_CUDA(cudaMemcpyAsync(h.data(), H2, h.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < count; p++) {
+    Fr acc = Fr::zero();
+    for (uint32_t c = NC2; c-- > 0;) acc = fp_add(fp_mul(acc, xs[p]), h[(size_t)p * NC2 + c]);
+    out[p] = acc;
+  }
+}
+
+static void store_canonical(uint8_t* dst, const Fr& mont) {
+  Fr c = fp_from_mont(mont);
+  memcpy(dst, c.v, 32);
+}
+
+// ---- round 1 (prover.py:86-119) -------------------------------------------------------------------------
+void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
+                   uint64_t n_public) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n;
+  cudaStream_t st = ctx->stream;
+  PB_CHECK(n_public <= n, "more public inputs than rows");
+  const uint8_t* src[3] = {hA, hB, hC};
+  for (int k = 0; k < 3; k++) upload_mont(ctx, P->lag[k], src[k], n);
+  // PI: Lagrange values -public_i (prover.py:57-62)
+  PB_CUDA(cudaMemsetAsync(P->pi_lag.p, 0, n * 32, st));
+  if (n_public) {
+    PB_CUDA(cudaMemcpyAsync(P->pi_lag.p, h_public, n_public * 32, cudaMemcpyHostToDevice, st));
+    fr_to_mont(ctx, P->pi_lag.as<Fr>(), P->pi_lag.as<Fr>(), n_public);
+    k_negate<<<PB_GRID(n_public, 128), 0, st>>>(P->pi_lag.as<Fr>(), n_public);
+    ctx->launches++;
+  }
+  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
+  k_gate_check<<<PB_GRID(n, 128), 0, st>>>(P->lag[0].as<Fr>(), P->lag[1].as<Fr>(), P->lag[2].as<Fr>(),
+                                          P->sel_lag[Prover::QL].as<Fr>(), P->sel_lag[Prover::QR].as<Fr>(),
+                                          P->sel_lag[Prover::QM].as<Fr>(), P->sel_lag[Prover::QO].as<Fr>(),
+                                          P->sel_lag[Prover::QC].as<Fr>(), P->pi_lag.as<Fr>(), n, P->flags.as<uint32_t>());
+  ctx->launches++;
+  for (int k = 0; k < 3; k++)
+    ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  ntt_run(ctx, P->pi_lag.as<Fr>(), P->coeff[4].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  PB_CHECK(read_flag(P, 0) == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
+  for (int k = 0; k < 3; k++) P->commit(P->coeff[k].as<Fr>(), n, P->proof.pts[k]);
+}
+
+// ---- round 2 (prover.py:121-152) -------------------------------------------------------------------------
+void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n;
+  cudaStream_t st = ctx->stream;
+  P->beta = fp_to_mont(beta_c);
+  P->gamma = fp_to_mont(gamma_c);
+  PermChallenges ch{P->beta, P->gamma};
+  Fr* num = P->tmp[0].as<Fr>();
+  Fr* den = P->tmp[1].as<Fr>();
+  k_perm_terms<<<PB_GRID(n, 128), 0, st>>>(P->lag[0].as<Fr>(), P->lag[1].as<Fr>(), P->lag[2].as<Fr>(),
+                                          P->sel_lag[Prover::S1].as<Fr>(), P->sel_lag[Prover::S2].as<Fr>(),
+                                          P->sel_lag[Prover::S3].as<Fr>(), P->roots.as<Fr>(), ch, n, num, den);
+  uint64_t T = (n + 7) / 8;
+  k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den, num, n, T);
+  uint32_t n_tiles = (uint32_t)((n + PB_PROD_TILE - 1) / PB_PROD_TILE);
+  PB_CHECK(n_tiles <= 65536, "group order too large for the product scan");
+  ctx->scratch[0].ensure((size_t)(n_tiles + 1) * 32);
+  Fr* tiles = ctx->scratch[0].as<Fr>();
+  k_prod_tiles<<<n_tiles, 256, 0, st>>>(num, n, tiles);
+  k_prod_scan_tiles<<<1, 256, 0, st>>>(tiles, n_tiles, tiles + n_tiles);
+  k_prod_apply<<<n_tiles, 256, 0, st>>>(num, n, tiles, P->lag[3].as<Fr>());
+  ctx->launches += 5;
+  Fr total;
+  PB_CUDA(cudaMemcpyAsync(&total, tiles + n_tiles, 32, cudaMemcpyDeviceToHost, st));
+  ntt_run(ctx, P->lag[3].as<Fr>(), P->coeff[3].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  PB_CUDA(cudaStreamSynchronize(st));
+  PB_CHECK(total == Fr::one(), "AssertionError: permutation grand product does not close, Z_n != 1 (prover.py:132)");
+  P->commit(P->coeff[3].as<Fr>(), n, P->proof.pts[3]);
+}
+
+// ---- round 3 (prover.py:154-226) -------------------------------------------------------------------------
+void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n, n4 = 4 * n;
+  cudaStream_t st = ctx->stream;
+  P->alpha = fp_to_mont(alpha_c);
+  P->fft_cofactor = fp_to_mont(cofactor_c);
+  for (int k = 0; k < 5; k++)
+    ntt_run(ctx, P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->log_n + 2, false, n, P->gpow.as<Fr>(), nullptr);
+  QuotientArgs q;
+  q.A = P->ext[0].as<Fr>(); q.B = P->ext[1].as<Fr>(); q.C = P->ext[2].as<Fr>(); q.Z = P->ext[3].as<Fr>();
+  q.PI = P->ext[4].as<Fr>();
+  q.QM = P->sel_ext[Prover::QM].as<Fr>(); q.QL = P->sel_ext[Prover::QL].as<Fr>(); q.QR = P->sel_ext[Prover::QR].as<Fr>();
+  q.QO = P->sel_ext[Prover::QO].as<Fr>(); q.QC = P->sel_ext[Prover::QC].as<Fr>();
+  q.S1 = P->sel_ext[Prover::S1].as<Fr>(); q.S2 = P->sel_ext[Prover::S2].as<Fr>(); q.S3 = P->sel_ext[Prover::S3].as<Fr>();
+  q.L0 = P->l0_ext.as<Fr>(); q.X = P->xs.as<Fr>();
+  for (int k = 0; k < 4; k++) q.zh_inv[k] = P->zh_inv[k];
+  q.alpha = P->alpha; q.alpha2 = fp_sqr(P->alpha); q.beta = P->beta; q.gamma = P->gamma; q.one = Fr::one();
+  q.n4 = n4;
+  k_quotient<<<PB_GRID(n4, 128), 0, st>>>(q, P->tq.as<Fr>());
+  ctx->launches++;
+  // back to coefficients: ifft(4n) then * g^-i (poly.py:169-177 with the fixed coset)
+  ntt_run(ctx, P->tq.as<Fr>(), P->tq.as<Fr>(), P->log_n + 2, true, n4, nullptr, P->ginv_pow.as<Fr>());
+  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
+  k_count_nonzero<<<PB_GRID(n, 256), 0, st>>>(P->tq.as<Fr>() + 3 * n, n, P->flags.as<uint32_t>());
+  ctx->launches++;
+  PB_CHECK(read_flag(P, 0) == 0, "AssertionError: quotient has degree >= 3n (prover.py:205-208)");
+  for (int k = 0; k < 3; k++) P->commit(P->tq.as<Fr>() + k * n, n, P->proof.pts[4 + k]);
+}
+
+// ---- round 4 (prover.py:228-239) -------------------------------------------------------------------------
+void prover_round4(Prover* P, const Fr& zeta_c) {
+  P->zeta = fp_to_mont(zeta_c);
+  Fr zw = fp_mul(P->zeta, fr_root_of_unity(P->log_n));
+  const Fr* polys[7] = {P->coeff[0].as<Fr>(), P->coeff[1].as<Fr>(), P->coeff[2].as<Fr>(),
+                        P->sel_coeff[Prover::S1].as<Fr>(), P->sel_coeff[Prover::S2].as<Fr>(),
+                        P->coeff[3].as<Fr>(), P->coeff[4].as<Fr>()};
+  Fr xs[7] = {P->zeta, P->zeta, P->zeta, P->zeta, P->zeta, zw, P->zeta};
+  Fr out[7];
+  eval_polys(P, 7, polys, xs, out);
+  for (int k = 0; k < 6; k++) { P->ev[k] = out[k]; store_canonical(P->proof.evals[k], out[k]); }
+  P->pi_ev = out[6];
+}
+
+// (num coefficients, n) / (X - point) -> quotient coefficients in place (n-point coset division)
+static void divide_linear(Prover* P, Fr* num, const Fr& point, Fr* den_buf) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n;
+  cudaStream_t st = ctx->stream;
+  ntt_run(ctx, num, num, P->log_n, false, n, P->gpow.as<Fr>(), nullptr);
+  k_coset_minus<<<PB_GRID(n, 256), 0, st>>>(P->roots.as<Fr>(), P->g, point, n, den_buf);
+  uint64_t T = (n + 7) / 8;
+  k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den_buf, num, n, T);
+  ctx->launches += 2;
+  ntt_run(ctx, num, num, P->log_n, true, n, nullptr, P->ginv_pow.as<Fr>());
+}
+
+// ---- round 5 (prover.py:241-306) -------------------------------------------------------------------------
+void prover_round5(Prover* P, const Fr& v_c) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n;
+  cudaStream_t st = ctx->stream;
+  P->v = fp_to_mont(v_c);
+  const Fr one = Fr::one();
+  const Fr &a = P->ev[0], &b = P->ev[1], &c = P->ev[2], &s1 = P->ev[3], &s2 = P->ev[4], &zw = P->ev[5];
+  const Fr &al = P->alpha, &be = P->beta, &ga = P->gamma, &zeta = P->zeta, &v = P->v;
+  Fr zn = fp_pow_u64(zeta, n);
+  Fr zh_ev = fp_sub(zn, one);                                                   // Z_H(zeta)
+  Fr l0_ev = fp_mul(zh_ev, fp_inv(fp_mul(fr_from_u64(n), fp_sub(zeta, one))));   // L0(zeta)
+  Fr bz = fp_mul(be, zeta);
+  Fr c1 = fp_mul(fp_mul(fp_mul(fp_add(fp_add(a, bz), ga), fp_add(fp_add(b, fp_dbl(bz)), ga)),
+                        fp_add(fp_add(c, fp_add(fp_dbl(bz), bz)), ga)), al);
+  Fr c2 = fp_mul(fp_mul(fp_mul(fp_add(fp_add(a, fp_mul(be, s1)), ga), fp_add(fp_add(b, fp_mul(be, s2)), ga)), al), zw);
+  Fr al2l0 = fp_mul(fp_sqr(al), l0_ev);
+  Fr v2 = fp_sqr(v), v3 = fp_mul(v2, v), v4 = fp_sqr(v2), v5 = fp_mul(v4, v);
+  // W_z numerator = R + v(A - a) + v^2(B - b) + v^3(C - c) + v^4(S1 - s1) + v^5(S2 - s2), R per SURVEY App. D
+  LinCombArgs L;
+  int k = 0;
+  auto add = [&](const Fr* vec, const Fr& w) { L.vec[k] = vec; L.w[k] = w; k++; };
+  add(P->sel_coeff[Prover::QL].as<Fr>(), a);
+  add(P->sel_coeff[Prover::QR].as<Fr>(), b);
+  add(P->sel_coeff[Prover::QM].as<Fr>(), fp_mul(a, b));
+  add(P->sel_coeff[Prover::QO].as<Fr>(), c);
+  add(P->sel_coeff[Prover::QC].as<Fr>(), one);
+  add(P->coeff[3].as<Fr>(), fp_add(c1, al2l0));                        // Z
+  add(P->sel_coeff[Prover::S3].as<Fr>(), fp_neg(fp_mul(c2, be)));
+  add(P->tq.as<Fr>(), fp_neg(zh_ev));                                  // T1
+  add(P->tq.as<Fr>() + n, fp_neg(fp_mul(zh_ev, zn)));                  // T2
+  add(P->tq.as<Fr>() + 2 * n, fp_neg(fp_mul(zh_ev, fp_sqr(zn))));      // T3
+  add(P->coeff[0].as<Fr>(), v);
+  add(P->coeff[1].as<Fr>(), v2);
+  add(P->coeff[2].as<Fr>(), v3);
+  add(P->sel_coeff[Prover::S1].as<Fr>(), v4);
+  add(P->sel_coeff[Prover::S2].as<Fr>(), v5);
+  L.count = k;
+  L.n = n;
+  // constant term: PI(zeta) - c2 (c + gamma) - alpha^2 L0(zeta) - v a - v^2 b - v^3 c - v^4 s1 - v^5 s2
+  Fr c0 = fp_sub(P->pi_ev, fp_mul(c2, fp_add(c, ga)));
+  c0 = fp_sub(c0, al2l0);
+  c0 = fp_sub(c0, fp_mul(v, a));
+  c0 = fp_sub(c0, fp_mul(v2, b));
+  c0 = fp_sub(c0, fp_mul(v3, c));
+  c0 = fp_sub(c0, fp_mul(v4, s1));
+  c0 = fp_sub(c0, fp_mul(v5, s2));
+  L.c0 = c0;
+  Fr* wz = P->tmp[0].as<Fr>();
+  k_lincomb<<<PB_GRID(n, 128), 0, st>>>(L, wz);
+  ctx->launches++;
+  divide_linear(P, wz, zeta, P->tmp[2].as<Fr>());
+  // W_zw numerator = Z - z_shifted_eval
+  LinCombArgs M;
+  M.vec[0] = P->coeff[3].as<Fr>(); M.w[0] = one; M.count = 1; M.n = n; M.c0 = fp_neg(zw);
+  Fr* wzw = P->tmp[1].as<Fr>();
+  k_lincomb<<<PB_GRID(n, 128), 0, st>>>(M, wzw);
+  ctx->launches++;
+  divide_linear(P, wzw, fp_mul(zeta, fr_root_of_unity(P->log_n)), P->tmp[2].as<Fr>());
+  // both quotients have degree <= n-2: the top coefficient must vanish (prover.py:288,299)
+  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
+  k_count_nonzero<<<1, 32, 0, st>>>(wz + (n - 1), 1, P->flags.as<uint32_t>());
+  k_count_nonzero<<<1, 32, 0, st>>>(wzw + (n - 1), 1, P->flags.as<uint32_t>());
+  ctx->launches += 2;
+  PB_CHECK(read_flag(P, 0) == 0, "AssertionError: opening quotient has degree >= n-1 (prover.py:288,299)");
+  P->commit(wz, n, P->proof.pts[7]);
+  P->commit(wzw, n, P->proof.pts[8]);
+}
+
+// canonical 768-byte proof: Proof.flatten() order (prover.py:18-35), G1 as x||y, every integer 32-byte
+// big-endian exactly as the transcript absorbs it (transcript.py:62-67)
+void prover_serialize(const Prover* P, uint8_t* out768) {
+  auto be = [](uint8_t* dst, const uint8_t* le) { for (int i = 0; i < 32; i++) dst[i] = le[31 - i]; };
+  uint8_t* o = out768;
+  for (int k = 0; k < 7; k++) { be(o, P->proof.pts[k]); be(o + 32, P->proof.pts[k] + 32); o += 64; }
+  for (int k = 0; k < 6; k++) { be(o, P->proof.evals[k]); o += 32; }
+  for (int k = 7; k < 9; k++) { be(o, P->proof.pts[k]); be(o + 32, P->proof.pts[k] + 32); o += 64; }
+}
+
+// prover.py:51-84
+void prover_prove(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
+                  uint64_t n_public, uint8_t* out768) {
+  Transcript tr("plonk");  // prover.py:53
+  prover_round1(P, hA, hB, hC, h_public, n_public);
+  tr.append_point_le("a_1", P->proof.pts[0]);
+  tr.append_point_le("b_1", P->proof.pts[1]);
+  tr.append_point_le("c_1", P->proof.pts[2]);
+  Fr beta = tr.get_and_append_challenge("beta");
+  Fr gamma = tr.get_and_append_challenge("gamma");
+  prover_round2(P, beta, gamma);
+  tr.append_point_le("z_1", P->proof.pts[3]);
+  Fr alpha = tr.get_and_append_challenge("alpha");
+  Fr cof = tr.get_and_append_challenge("fft_cofactor");
+  prover_round3(P, alpha, cof);
+  tr.append_point_le("t_lo_1", P->proof.pts[4]);
+  tr.append_point_le("t_mid_1", P->proof.pts[5]);
+  tr.append_point_le("t_hi_1", P->proof.pts[6]);
+  Fr zeta = tr.get_and_append_challenge("zeta");
+  prover_round4(P, zeta);
+  static const char* ev_labels[6] = {"a_eval", "b_eval", "c_eval", "s1_eval", "s2_eval", "z_shifted_eval"};
+  for (int k = 0; k < 6; k++) tr.append_scalar_le(ev_labels[k], P->proof.evals[k]);
+  Fr v = tr.get_and_append_challenge("v");
+  prover_round5(P, v);
+  prover_serialize(P, out768);
+}
+
+}  // namespace pb200

@@ -1,0 +1,54 @@
+// Prover state shared between prover.cu (the rounds) and capi.cu (the C ABI accessors).
+#pragma once
+#include "common.cuh"
+
+namespace pb200 {
+
+struct Srs;
+void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
+
+struct Proof {
+  uint8_t pts[9][64];    // a_1 b_1 c_1 z_1 t_lo t_mid t_hi W_z W_zw  (canonical LE x||y)
+  uint8_t evals[6][32];  // a b c s1 s2 z_shifted (canonical LE)
+};
+
+struct Prover {
+  Context* ctx;
+  Srs* srs;
+  int log_n;
+  uint64_t n;
+  // per-circuit (all Montgomery)
+  DevBuf sel_coeff[8];   // QM QL QR QO QC S1 S2 S3, coefficient form
+  DevBuf sel_lag[8];     // same, Lagrange values (QM..QC for the gate check, S1..S3 for round 2)
+  DevBuf sel_ext[8];     // same, on the fixed 4n coset
+  DevBuf roots;          // w^i, i < n
+  DevBuf gpow;           // g^i, i < n            (coset shift on load)
+  DevBuf ginv_pow;       // g^-i, i < 4n          (undo the shift on store)
+  DevBuf xs;             // g * mu^j, j < 4n
+  DevBuf l0_ext;         // L0 on the coset
+  Fr g, g_inv, zh_inv[4];
+  // per-proof state
+  DevBuf lag[4];         // A B C Z Lagrange
+  DevBuf coeff[5];       // a b c z pi coefficients
+  DevBuf pi_lag;
+  DevBuf ext[5];         // A B C Z PI on the coset
+  DevBuf tq;             // quotient evaluations / coefficients (4n)
+  DevBuf tmp[4];
+  DevBuf flags;
+  Fr beta, gamma, alpha, fft_cofactor, zeta, v;   // Montgomery
+  Fr ev[6];                                      // Montgomery evaluations (round 4)
+  Fr pi_ev;
+  Proof proof;
+
+  enum { QM = 0, QL, QR, QO, QC, S1, S2, S3 };
+
+  void commit(const Fr* d_coeffs, uint64_t m, uint8_t* out_xy) {
+    int ident = 0;
+    srs_msm(ctx, srs, d_coeffs, m, true, out_xy, &ident);
+    // transcript.py:65-67 cannot absorb the identity (item[0] on None); mirror that as an error
+    PB_CHECK(!ident, "commitment is the point at infinity (unsupported by the reference transcript)");
+  }
+};
+
+
+}  // namespace pb200
