@@ -38,6 +38,11 @@ void pb200_ctx_destroy(pb200_ctx* ctx);
 int pb200_ctx_sync(pb200_ctx* ctx);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t pb200_ctx_launches(pb200_ctx* ctx);
+/* per-kernel device timing with CUDA events on the launching stream (bench.py's roofline object).
+ * enable != 0 clears the records and starts recording.  category 0: MSM bucket accumulation kernel,
+ * 1: NTT pass kernel.  Returns the summed duration and the number of launches recorded. */
+int pb200_ctx_timing(pb200_ctx* ctx, int enable);
+int pb200_ctx_timing_read(pb200_ctx* ctx, int category, double* total_ms, uint64_t* count);
 /* the context's CUDA stream (cudaStream_t) so callers can time with events on it */
 void* pb200_ctx_stream(pb200_ctx* ctx);
 
@@ -79,6 +84,12 @@ int pb200_g1_msm_host(pb200_ctx* ctx, const uint8_t* h_points, const uint8_t* h_
 /* setup.py:16-22  Setup.powers_of_x.  h_points: n affine points (canonical).  precompute != 0 builds the
  * fixed-base window table in HBM (size ceil(256/c) * n * 64 bytes). */
 int pb200_srs_create(pb200_ctx* ctx, const uint8_t* h_points, uint64_t n, int precompute, pb200_srs** out);
+/* Structured test SRS generated on the device: points [tau^i]G, i < n, for a known (toxic) tau --
+ * the 2^20 / 2^22 configurations need more powers than the reference's shipped .ptau holds
+ * (setup.py:27 reads 2^11).  h_tau: canonical 32-byte Fr. */
+int pb200_srs_generate(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out);
+/* copy `count` points starting at `first` back to the host (canonical x||y) */
+int pb200_srs_export(pb200_ctx* ctx, pb200_srs* srs, uint8_t* h_points, uint64_t first, uint64_t count);
 void pb200_srs_destroy(pb200_srs* srs);
 uint64_t pb200_srs_size(pb200_srs* srs);
 /* setup.py:66-72  Setup.commit(values): values in the LAGRANGE basis -> ifft -> MSM with powers_of_x.
@@ -104,6 +115,9 @@ void pb200_prover_destroy(pb200_prover* p);
  * Fails (error string starts with "AssertionError") where the reference's asserts would. */
 int pb200_prover_prove(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
                        const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768);
+/* same, with the wire values already resident in HBM (canonical form, n x 32 bytes each) */
+int pb200_prover_prove_device(pb200_prover* p, const void* d_A, const void* d_B, const void* d_C,
+                              const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768);
 /* the individual rounds, challenges supplied by the caller's transcript; outputs little-endian */
 int pb200_prover_round1(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
                         const uint8_t* h_public, uint64_t n_public, uint8_t* h_abc_xy /*3*64*/);   /* prover.py:86 */

@@ -34,6 +34,8 @@ def _load():
         "pb200_ctx_sync": (I, [V]),
         "pb200_ctx_launches": (U64, [V]),
         "pb200_ctx_stream": (V, [V]),
+        "pb200_ctx_timing": (I, [V, I]),
+        "pb200_ctx_timing_read": (I, [V, I, P(ctypes.c_double), P(U64)]),
         "pb200_fr_to_mont": (I, [V, V, V, U64]),
         "pb200_fr_from_mont": (I, [V, V, V, U64]),
         "pb200_fr_ntt": (I, [V, V, V, U, I]),
@@ -47,6 +49,8 @@ def _load():
         "pb200_g1_msm": (I, [V, V, V, U64, V, P(I)]),
         "pb200_g1_msm_host": (I, [V, V, V, U64, V, P(I)]),
         "pb200_srs_create": (I, [V, V, U64, I, P(V)]),
+        "pb200_srs_generate": (I, [V, V, U64, I, P(V)]),
+        "pb200_srs_export": (I, [V, V, V, U64, U64]),
         "pb200_srs_destroy": (None, [V]),
         "pb200_srs_size": (U64, [V]),
         "pb200_srs_commit_lagrange": (I, [V, V, V, U, V, P(I)]),
@@ -55,6 +59,7 @@ def _load():
         "pb200_prover_create": (I, [V, V, U, V, P(V)]),
         "pb200_prover_destroy": (None, [V]),
         "pb200_prover_prove": (I, [V, V, V, V, V, U64, V]),
+        "pb200_prover_prove_device": (I, [V, V, V, V, V, U64, V]),
         "pb200_prover_round1": (I, [V, V, V, V, V, U64, V]),
         "pb200_prover_round2": (I, [V, V, V, V]),
         "pb200_prover_round3": (I, [V, V, V, V]),

@@ -22,6 +22,8 @@ float bench_modmul(Context* ctx, int field, uint64_t threads, uint32_t iters);
 struct Srs;
 Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precompute);
 void srs_destroy(Srs* s);
+Srs* srs_generate(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute);
+void srs_export(Context* ctx, Srs* srs, uint8_t* h_points, uint64_t first, uint64_t count);
 void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
 uint64_t srs_size(Srs* s);
 uint32_t msm_default_window(uint64_t n, bool fixed_base);
@@ -32,9 +34,9 @@ void affine_to_mont(Context* ctx, const G1Affine* in, G1Affine* out, uint64_t n)
 Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk);
 void prover_destroy(Prover* p);
 void prover_prove(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
-                  uint64_t n_public, uint8_t* out768);
+                  uint64_t n_public, uint8_t* out768, bool wires_on_device);
 void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
-                   uint64_t n_public);
+                   uint64_t n_public, bool wires_on_device);
 void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c);
 void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c);
 void prover_round4(Prover* P, const Fr& zeta_c);
@@ -114,6 +116,33 @@ int pb200_ctx_sync(pb200_ctx* ctx) {
 }
 
 uint64_t pb200_ctx_launches(pb200_ctx* ctx) { return C(ctx)->launches; }
+
+int pb200_ctx_timing(pb200_ctx* ctx, int enable) {
+  PB_API_BEGIN
+  Context* c = C(ctx);
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& v : c->timed) {
+    for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    v.clear();
+  }
+  c->timing = enable != 0;
+  PB_API_END
+}
+int pb200_ctx_timing_read(pb200_ctx* ctx, int category, double* total_ms, uint64_t* count) {
+  PB_API_BEGIN
+  Context* c = C(ctx);
+  PB_CHECK(category >= 0 && category < 4, "bad timing category");
+  PB_CUDA(cudaStreamSynchronize(c->stream));
+  double t = 0;
+  for (auto& pr : c->timed[category]) {
+    float ms = 0;
+    PB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    t += ms;
+  }
+  *total_ms = t;
+  *count = c->timed[category].size();
+  PB_API_END
+}
 void* pb200_ctx_stream(pb200_ctx* ctx) { return (void*)C(ctx)->stream; }
 
 int pb200_fr_to_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n) {
@@ -257,6 +286,17 @@ int pb200_srs_create(pb200_ctx* ctx, const uint8_t* h_points, uint64_t n, int pr
   *out = reinterpret_cast<pb200_srs*>(srs_create(C(ctx), h_points, n, precompute));
   PB_API_END
 }
+int pb200_srs_generate(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out) {
+  PB_API_BEGIN
+  PB_CHECK(n > 0, "empty SRS");
+  *out = reinterpret_cast<pb200_srs*>(srs_generate(C(ctx), load_fr_canonical(h_tau), n, precompute));
+  PB_API_END
+}
+int pb200_srs_export(pb200_ctx* ctx, pb200_srs* srs, uint8_t* h_points, uint64_t first, uint64_t count) {
+  PB_API_BEGIN
+  srs_export(C(ctx), reinterpret_cast<Srs*>(srs), h_points, first, count);
+  PB_API_END
+}
 void pb200_srs_destroy(pb200_srs* srs) { srs_destroy(reinterpret_cast<Srs*>(srs)); }
 uint64_t pb200_srs_size(pb200_srs* srs) { return srs_size(reinterpret_cast<Srs*>(srs)); }
 
@@ -298,14 +338,21 @@ void pb200_prover_destroy(pb200_prover* p) { prover_destroy(reinterpret_cast<Pro
 int pb200_prover_prove(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
                        const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768) {
   PB_API_BEGIN
-  prover_prove(reinterpret_cast<Prover*>(p), h_A, h_B, h_C, h_public, n_public, h_proof768);
+  prover_prove(reinterpret_cast<Prover*>(p), h_A, h_B, h_C, h_public, n_public, h_proof768, false);
+  PB_API_END
+}
+int pb200_prover_prove_device(pb200_prover* p, const void* d_A, const void* d_B, const void* d_C,
+                              const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768) {
+  PB_API_BEGIN
+  prover_prove(reinterpret_cast<Prover*>(p), (const uint8_t*)d_A, (const uint8_t*)d_B, (const uint8_t*)d_C, h_public,
+               n_public, h_proof768, true);
   PB_API_END
 }
 int pb200_prover_round1(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
                         const uint8_t* h_public, uint64_t n_public, uint8_t* h_abc_xy) {
   PB_API_BEGIN
   Prover* P = reinterpret_cast<Prover*>(p);
-  prover_round1(P, h_A, h_B, h_C, h_public, n_public);
+  prover_round1(P, h_A, h_B, h_C, h_public, n_public, false);
   memcpy(h_abc_xy, P->proof.pts[0], 3 * 64);
   PB_API_END
 }

@@ -73,6 +73,21 @@ struct Context {
   std::map<int, std::unique_ptr<NttPlan>> plans;  // key: log_n * 2 + inverse
   DevBuf scratch[8];                               // reusable temporaries
   uint64_t launches = 0;                           // kernels launched through this context
+  // optional per-kernel timing (bench.py roofline): CUDA event pairs on the launching stream
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed[4];  // 0: MSM bucket accumulate, 1: NTT passes
+  void time_begin(int cat) {
+    if (!timing) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, stream);
+    timed[cat].push_back({a, b});
+  }
+  void time_end(int cat) {
+    if (!timing) return;
+    cudaEventRecord(timed[cat].back().second, stream);
+  }
   Context();
   ~Context();
 };

@@ -339,6 +339,15 @@ __global__ void k_affine_to_mont(const G1Affine* in, G1Affine* out, uint64_t n) 
   out[i] = p;
 }
 
+__global__ void k_affine_from_mont(const G1Affine* in, G1Affine* out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = in[i];
+  p.x = fp_from_mont(p.x);
+  p.y = fp_from_mont(p.y);
+  out[i] = p;
+}
+
 // out[i] = 2^c * in[i] as XYZZ
 __global__ void __launch_bounds__(128) k_window_step(const G1Affine* in, G1XYZZ* out, uint64_t n, uint32_t c) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,8 +492,10 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
     PB_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)g.nb * sizeof(G1XYZZ), st));
     PB_CUDA(cudaMemsetAsync(own_slot, 0xff, (size_t)n_seg * 4, st));
     PB_CUDA(cudaMemsetAsync(heavy_count, 0, 16, st));
+    ctx->time_begin(0);
     k_msm_seg_accumulate<<<(n_seg + 127) / 128, 128, 0, st>>>(points, offsets.as<uint32_t>(), sorted.as<uint32_t>(),
                                                              g.nb, L, buckets.as<G1XYZZ>(), slots, slot_bucket, own_slot);
+    ctx->time_end(0);
     k_msm_stitch<<<(n_seg + 127) / 128, 128, 0, st>>>(offsets.as<uint32_t>(), g.nb, L, n_seg, slots, slot_bucket,
                                                      own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, 16);
     k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, buckets.as<G1XYZZ>());
@@ -502,6 +513,8 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
 }
 
 // ---- SRS --------------------------------------------------------------------------------
+static void srs_finish(Context* ctx, Srs* srs, int precompute);
+
 // h_points: n affine points, canonical little-endian (x || y), none the identity
 Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precompute) {
   auto srs = std::make_unique<Srs>();
@@ -511,6 +524,14 @@ Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precomput
   PB_CUDA(cudaMemcpyAsync(raw.p, h_points, n * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
   k_affine_to_mont<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(raw.as<G1Affine>(), srs->base.as<G1Affine>(), n);
   ctx->launches++;
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  srs_finish(ctx, srs.get(), precompute);
+  return srs.release();
+}
+
+// builds the fixed-base window table 2^(c*w) * P_i, w < W, in HBM
+static void srs_finish(Context* ctx, Srs* srs, int precompute) {
+  const uint64_t n = srs->n;
   if (precompute) {
     uint32_t c = msm_default_window(n, true);
     uint32_t W = windows_for(c);
@@ -528,12 +549,80 @@ Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precomput
     }
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  PB_CUDA(cudaStreamSynchronize(ctx->stream));
   PB_CUDA(cudaGetLastError());
-  return srs.release();
 }
 
 void srs_destroy(Srs* s) { delete s; }
+
+
+// ---- structured SRS generation: [tau^i] G for i < n (setup.py:16-22 `powers_of_x` for a known test tau) --
+// Fixed-base multiplication with byte windows: table[w][d-1] = d * 2^(8w) * G (32 x 255 affine points),
+// then point_i = sum_w table[w][byte_w(tau^i)].
+__global__ void __launch_bounds__(128) k_fb_table(G1XYZZ* out) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 32 * 255) return;
+  uint32_t w = t / 255, d = t % 255 + 1;
+  G1Affine g;
+  g.x = Fq::one();
+  g.y = fp_add(Fq::one(), Fq::one());  // generator (1, 2)
+  G1XYZZ gx = g1_from_affine(g);
+  G1XYZZ r = G1XYZZ::identity();
+  for (int i = 7; i >= 0; i--) {
+    g1_double(r);
+    if ((d >> i) & 1) g1_add(r, gx);
+  }
+  for (uint32_t k = 0; k < 8 * w; k++) g1_double(r);
+  out[t] = r;
+}
+
+__global__ void __launch_bounds__(128) k_fb_mul(const G1Affine* table, const Fr* scalars_mont, uint64_t n, G1XYZZ* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = fp_from_mont(scalars_mont[i]);
+  G1XYZZ acc = G1XYZZ::identity();
+  for (uint32_t w = 0; w < 32; w++) {
+    uint32_t d = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+    if (d) {
+      G1Affine p = ld_affine(table + w * 255 + (d - 1));
+      g1_add_mixed(acc, p);
+    }
+  }
+  out[i] = acc;
+}
+
+void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
+static void srs_finish(Context* ctx, Srs* srs, int precompute);
+
+// tau: canonical Fr; generates n powers on the device
+Srs* srs_generate(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute) {
+  auto srs = std::make_unique<Srs>();
+  srs->n = n;
+  srs->base.alloc(n * sizeof(G1Affine));
+  cudaStream_t st = ctx->stream;
+  DevBuf tab_x(32 * 255 * sizeof(G1XYZZ)), tab(32 * 255 * sizeof(G1Affine));
+  k_fb_table<<<(32 * 255 + 127) / 128, 128, 0, st>>>(tab_x.as<G1XYZZ>());
+  k_batch_to_affine<<<((32 * 255 + 15) / 16 + 127) / 128, 128, 0, st>>>(tab_x.as<G1XYZZ>(), tab.as<G1Affine>(), 32 * 255);
+  DevBuf pw(n * 32), pts(n * sizeof(G1XYZZ));
+  launch_powers(ctx, pw.as<Fr>(), n, fp_to_mont(tau_canonical), Fr::one());
+  k_fb_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tab.as<G1Affine>(), pw.as<Fr>(), n, pts.as<G1XYZZ>());
+  uint64_t threads = (n + 15) / 16;
+  k_batch_to_affine<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(pts.as<G1XYZZ>(), srs->base.as<G1Affine>(), n);
+  ctx->launches += 4;
+  PB_CUDA(cudaStreamSynchronize(st));
+  srs_finish(ctx, srs.get(), precompute);
+  return srs.release();
+}
+
+// copies the (canonical) affine points back to the host
+void srs_export(Context* ctx, Srs* srs, uint8_t* h_points, uint64_t first, uint64_t count) {
+  PB_CHECK(first + count <= srs->n, "SRS export out of range");
+  DevBuf tmp(count * sizeof(G1Affine));
+  k_affine_from_mont<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(srs->base.as<G1Affine>() + first,
+                                                                          tmp.as<G1Affine>(), count);
+  ctx->launches++;
+  PB_CUDA(cudaMemcpyAsync(h_points, tmp.p, count * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
 
 // commit to m <= n coefficients (device, Montgomery or canonical form)
 void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity) {

@@ -408,7 +408,9 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
     q.in_scale = (i == 0) ? in_scale : nullptr;
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
+    ctx->time_begin(1);
     k_ntt_pass<<<(unsigned)ps.tiles, 256, smem, ctx->stream>>>(q);
+    ctx->time_end(1);
     ctx->launches++;
   }
   PB_CUDA(cudaGetLastError());

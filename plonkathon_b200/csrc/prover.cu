@@ -368,13 +368,16 @@ static void store_canonical(uint8_t* dst, const Fr& mont) {
 
 // ---- round 1 (prover.py:86-119) -------------------------------------------------------------------------
 void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
-                   uint64_t n_public) {
+                   uint64_t n_public, bool wires_on_device) {
   Context* ctx = P->ctx;
   const uint64_t n = P->n;
   cudaStream_t st = ctx->stream;
   PB_CHECK(n_public <= n, "more public inputs than rows");
   const uint8_t* src[3] = {hA, hB, hC};
-  for (int k = 0; k < 3; k++) upload_mont(ctx, P->lag[k], src[k], n);
+  for (int k = 0; k < 3; k++) {
+    if (wires_on_device) fr_to_mont(ctx, reinterpret_cast<const Fr*>(src[k]), P->lag[k].as<Fr>(), n);
+    else upload_mont(ctx, P->lag[k], src[k], n);
+  }
   // PI: Lagrange values -public_i (prover.py:57-62)
   PB_CUDA(cudaMemsetAsync(P->pi_lag.p, 0, n * 32, st));
   if (n_public) {
@@ -565,9 +568,9 @@ void prover_serialize(const Prover* P, uint8_t* out768) {
 
 // prover.py:51-84
 void prover_prove(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
-                  uint64_t n_public, uint8_t* out768) {
+                  uint64_t n_public, uint8_t* out768, bool wires_on_device) {
   Transcript tr("plonk");  // prover.py:53
-  prover_round1(P, hA, hB, hC, h_public, n_public);
+  prover_round1(P, hA, hB, hC, h_public, n_public, wires_on_device);
   tr.append_point_le("a_1", P->proof.pts[0]);
   tr.append_point_le("b_1", P->proof.pts[1]);
   tr.append_point_le("c_1", P->proof.pts[2]);

@@ -10,7 +10,7 @@ from typing import Optional
 
 from . import _lib
 from .curve import Scalar, _pt_bytes, _pt_from
-from .field import FIELD_MODULUS, FQ
+from .field import CURVE_ORDER, FIELD_MODULUS, FQ
 from .poly import Basis, Polynomial, _log2_exact, scalars_to_bytes
 
 SETUP_FILE_G1_STARTPOS = 80  # setup.py:11
@@ -36,14 +36,44 @@ class VerificationKey:
 
 class Setup:
     def __init__(self, powers_of_x, X2, ctx: Optional[_lib.Context] = None, precompute: bool = True):
-        self.powers_of_x = powers_of_x
+        self._powers = list(powers_of_x)
+        self._n = len(self._powers)
         self.X2 = X2
         self.ctx = ctx or _lib.default_context()
-        raw = b"".join(_pt_bytes(p) for p in powers_of_x)
+        raw = b"".join(_pt_bytes(p) for p in self._powers)
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().pb200_srs_create(self.ctx.handle, raw, len(powers_of_x), 1 if precompute else 0,
+        _lib.check(_lib.lib().pb200_srs_create(self.ctx.handle, raw, self._n, 1 if precompute else 0,
                                                ctypes.byref(h)))
         self._srs = h
+
+    @classmethod
+    def generate(cls, tau: int, n: int, ctx: Optional[_lib.Context] = None, precompute: bool = True):
+        """Structured test SRS [tau^i]G, i < n, generated on the GPU (the shipped .ptau stops at 2^11 powers,
+        setup.py:27).  ``powers_of_x`` is materialised lazily; X2 is not available (verification only)."""
+        self = cls.__new__(cls)
+        self._powers = None
+        self._n = n
+        self.X2 = None
+        self.tau = tau % CURVE_ORDER
+        self.ctx = ctx or _lib.default_context()
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().pb200_srs_generate(self.ctx.handle, self.tau.to_bytes(32, "little"), n,
+                                                 1 if precompute else 0, ctypes.byref(h)))
+        self._srs = h
+        return self
+
+    def export_points(self, first: int, count: int):
+        buf = ctypes.create_string_buffer(64 * count)
+        _lib.check(_lib.lib().pb200_srs_export(self.ctx.handle, self._srs, buf, first, count))
+        raw = buf.raw
+        return [(FQ(int.from_bytes(raw[64 * k:64 * k + 32], "little")),
+                 FQ(int.from_bytes(raw[64 * k + 32:64 * k + 64], "little"))) for k in range(count)]
+
+    @property
+    def powers_of_x(self):
+        if self._powers is None:
+            self._powers = self.export_points(0, self._n)
+        return self._powers
 
     def __del__(self):
         try:
@@ -79,7 +109,7 @@ class Setup:
         """setup.py:66-72."""
         assert values.basis == Basis.LAGRANGE
         n = len(values.values)
-        if n > len(self.powers_of_x):
+        if n > self._n:
             raise Exception("Not enough powers in setup")
         raw = scalars_to_bytes(values.values)
         out = ctypes.create_string_buffer(64)

@@ -269,3 +269,32 @@ def test_prove_rejects_bad_witness(pb, setup):
     bad[15] = (bad[15] + 1) % R
     with pytest.raises(AssertionError):  # prover.py:108-116
         prover.prove_arrays(arr["A"], arr["B"], bad, ints(entry["public"]))
+
+
+# ------------------------------------------------------------------ synthetic SRS + circuits
+TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+
+
+def test_srs_generate_matches_oracle(pb):
+    s = pb.Setup.generate(TAU, 300, precompute=False)
+    got = [(p[0].n, p[1].n) for p in s.export_points(0, 300)]
+    cur = O.G1
+    for i in range(300):
+        assert got[i] == cur, i
+        cur = O.g1_multiply(cur, TAU)
+
+
+@pytest.mark.parametrize("log_n,fill", [(4, 1.0), (7, 0.9)])
+def test_prove_synthetic_vs_oracle(pb, log_n, fill):
+    """synthetic circuit family used by bench.py, small instance: GPU proof bytes == oracle proof bytes"""
+    from plonkathon_b200 import synthetic as syn
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=log_n, n_public=2, fill=fill)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    raw = pb.Prover.from_arrays(setup, n, pk).prove_arrays(A, B, C, public)
+    S1, S2, S3 = syn.permutation_polys(c.wire_L, c.wire_R, c.wire_O, n, c.n_constraints)
+    opk = O.Preprocessed(n, c.QM, c.QL, c.QR, c.QO, c.QC, S1, S2, S3)
+    osetup = O.Setup([(p[0].n, p[1].n) for p in setup.powers_of_x], None)
+    a, b, cc = c.wires_values()
+    assert raw == O.proof_bytes(O.Prover(osetup, opk).prove(a, b, cc, c.public_values()))
