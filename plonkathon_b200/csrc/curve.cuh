@@ -87,6 +87,37 @@ PB_HD void g1_add_mixed(G1XYZZ& acc, const G1Affine& p) {
   acc.ZZZ = fp_mul(acc.ZZZ, PPP);
 }
 
+// acc += p with (almost) uniform control flow for SIMT execution: every lane runs the same 8M + 2S
+// sequence; an empty accumulator is handled by a select at the end instead of an early return, and only
+// the rare P == +-Q cases branch.
+PB_HD void g1_add_mixed_uniform(G1XYZZ& acc, const G1Affine& p) {
+  const bool was_inf = acc.is_inf();
+  Fq U2 = fp_mul(p.x, acc.ZZ);
+  Fq S2 = fp_mul(p.y, acc.ZZZ);
+  Fq Pd = fp_sub(U2, acc.X);
+  Fq Rd = fp_sub(S2, acc.Y);
+  if (!was_inf && Pd.is_zero()) {
+    if (Rd.is_zero()) g1_double_affine(acc, p);
+    else acc = G1XYZZ::identity();
+    return;
+  }
+  Fq PP = fp_sqr(Pd);
+  Fq PPP = fp_mul(Pd, PP);
+  Fq Q = fp_mul(acc.X, PP);
+  Fq X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
+  Fq Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(acc.Y, PPP));
+  Fq ZZ3 = fp_mul(acc.ZZ, PP);
+  Fq ZZZ3 = fp_mul(acc.ZZZ, PPP);
+  const Fq one = Fq::one();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc.X.v[i] = was_inf ? p.x.v[i] : X3.v[i];
+    acc.Y.v[i] = was_inf ? p.y.v[i] : Y3.v[i];
+    acc.ZZ.v[i] = was_inf ? one.v[i] : ZZ3.v[i];
+    acc.ZZZ.v[i] = was_inf ? one.v[i] : ZZZ3.v[i];
+  }
+}
+
 // acc += q
 PB_HD void g1_add(G1XYZZ& acc, const G1XYZZ& q) {
   if (q.is_inf()) return;

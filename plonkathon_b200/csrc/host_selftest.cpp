@@ -46,6 +46,13 @@ int hs_curve_op(int op, const uint32_t* acc_in, const uint32_t* other, int other
       if (!other_inf) g1_add_mixed(acc, p);
       break;
     }
+    case 4: {
+      G1Affine p;
+      memcpy(&p.x, other, 32);
+      memcpy(&p.y, other + 8, 32);
+      if (!other_inf) g1_add_mixed_uniform(acc, p);
+      break;
+    }
     case 1: {
       G1XYZZ q;
       memcpy(&q, other, sizeof(q));

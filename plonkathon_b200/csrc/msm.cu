@@ -191,31 +191,33 @@ __global__ void __launch_bounds__(128) k_msm_seg_accumulate(const G1Affine* poin
   const uint32_t s = (uint32_t)s64;
   const uint32_t e = (uint32_t)min((uint64_t)M, s64 + L);
   uint32_t b = upper_bound_u32(offsets, nb + 1, s) - 1;  // offsets[b] <= s < offsets[b+1]
-  uint32_t pos = s;
+  uint32_t bstart = offsets[b], bend = offsets[b + 1];
   bool first = true;
-  while (pos < e) {
-    const uint32_t bstart = offsets[b], bend = offsets[b + 1];
-    const uint32_t run_end = min(bend, e);
-    G1XYZZ acc = G1XYZZ::identity();
-    for (; pos < run_end; pos++) {
-      uint32_t v = __ldg(sorted + pos);
-      G1Affine p = ld_affine(points + (v & 0x7fffffffu));
-      if (v >> 31) p.y = fp_neg(p.y);
-      g1_add_mixed(acc, p);
-    }
-    if (bstart >= s && bend <= e) {
-      buckets[b] = acc;
-    } else {
-      uint32_t slot = first ? 2 * t : 2 * t + 1;
-      slots[slot] = acc;
-      slot_bucket[slot] = b;
-      if (bstart >= s) own_slot[t] = slot;  // the bucket starts here and continues past e
-    }
-    first = false;
-    if (pos < e) {
+  G1XYZZ acc = G1XYZZ::identity();
+  // one flat loop over the segment: every lane does one mixed addition per iteration (uniform control
+  // flow); run boundaries only cost a short predicated flush
+  for (uint32_t pos = s; pos <= e; pos++) {
+    if (pos == bend || pos == e) {
+      if (bstart >= s && bend <= e) {
+        buckets[b] = acc;
+      } else {
+        uint32_t slot = first ? 2 * t : 2 * t + 1;
+        slots[slot] = acc;
+        slot_bucket[slot] = b;
+        if (bstart >= s) own_slot[t] = slot;  // the bucket starts here and continues past e
+      }
+      if (pos == e) break;
+      first = false;
+      acc = G1XYZZ::identity();
       b++;
       while (offsets[b + 1] <= pos) b++;  // skip empty buckets
+      bstart = offsets[b];
+      bend = offsets[b + 1];
     }
+    uint32_t v = __ldg(sorted + pos);
+    G1Affine p = ld_affine(points + (v & 0x7fffffffu));
+    if (v >> 31) p.y = fp_neg(p.y);
+    g1_add_mixed_uniform(acc, p);
   }
 }
 
@@ -307,12 +309,15 @@ __global__ void __launch_bounds__(128) k_bucket_groups(const G1XYZZ* buckets, ui
   out[t] = sum;
 }
 
-// out[w] = sum of in[w * per + 0 .. per)   (one block per w)
+// out[w * gridDim.x + blockIdx.x] = sum of this block's 128-point slice of in[w * per .. (w+1) * per)
+// (blockIdx.y = w).  Applied twice it sums up to 16384 points per window with 7-deep trees only.
 __global__ void __launch_bounds__(128) k_sum_points(const G1XYZZ* in, uint32_t per, G1XYZZ* out) {
   __shared__ G1XYZZ sh[128];
-  const G1XYZZ* base = in + (uint64_t)blockIdx.x * per;
+  const G1XYZZ* base = in + (uint64_t)blockIdx.y * per;
+  uint32_t chunk = (per + gridDim.x - 1) / gridDim.x;
+  uint32_t lo = blockIdx.x * chunk, hi = min(lo + chunk, per);
   G1XYZZ acc = G1XYZZ::identity();
-  for (uint32_t i = threadIdx.x; i < per; i += blockDim.x) {
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     G1XYZZ v = base[i];
     g1_add(acc, v);
   }
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(128) k_sum_points(const G1XYZZ* in, uint32_t p
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+  if (threadIdx.x == 0) out[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
 }
 
 // affine points: canonical <-> Montgomery (both coordinates)
@@ -459,9 +464,9 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   counts.ensure((size_t)g.nb * 4);
   offsets.ensure((size_t)(g.nb + 1) * 4);
   buckets.ensure((size_t)g.nb * sizeof(G1XYZZ));
-  uint32_t gsz = g.half >= 64 ? 64 : g.half;
+  uint32_t gsz = g.half >= 32 ? 32 : g.half;
   uint32_t n_groups = g.nb / gsz;
-  groups.ensure((size_t)n_groups * sizeof(G1XYZZ));
+  groups.ensure(((size_t)n_groups + (size_t)n_windows_out * 1024) * sizeof(G1XYZZ));
   wsums.ensure((size_t)n_windows_out * sizeof(G1XYZZ) + 8192 * 4);
 
   cudaStream_t st = ctx->stream;
@@ -503,7 +508,18 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   }
   k_bucket_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(buckets.as<G1XYZZ>(), g.half, gsz, n_groups,
                                                          groups.as<G1XYZZ>());
-  k_sum_points<<<n_windows_out, 128, 0, st>>>(groups.as<G1XYZZ>(), g.half / gsz, wsums.as<G1XYZZ>());
+  {
+    uint32_t per = g.half / gsz;                       // group results per window
+    uint32_t mid = per > 128 ? (per + 127) / 128 : 1;  // first-level blocks per window
+    G1XYZZ* level1 = groups.as<G1XYZZ>() + n_groups;
+    if (mid > 1) {
+      k_sum_points<<<dim3(mid, n_windows_out), 128, 0, st>>>(groups.as<G1XYZZ>(), per, level1);
+      k_sum_points<<<dim3(1, n_windows_out), 128, 0, st>>>(level1, mid, wsums.as<G1XYZZ>());
+      ctx->launches++;
+    } else {
+      k_sum_points<<<dim3(1, n_windows_out), 128, 0, st>>>(groups.as<G1XYZZ>(), per, wsums.as<G1XYZZ>());
+    }
+  }
   ctx->launches += 6;
   PB_CUDA(cudaGetLastError());
   std::vector<G1XYZZ> ws(n_windows_out);

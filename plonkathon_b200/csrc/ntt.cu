@@ -161,7 +161,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_ntt_pass(PassParams p) {
+__global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t B = 1u << p.log_b, CC = 1u << p.log_cc, TE = B << p.log_cc;
   uint4* s_lo = reinterpret_cast<uint4*>(smem_raw);
@@ -409,7 +409,7 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
     ctx->time_begin(1);
-    k_ntt_pass<<<(unsigned)ps.tiles, 256, smem, ctx->stream>>>(q);
+    k_ntt_pass<<<(unsigned)ps.tiles, 512, smem, ctx->stream>>>(q);
     ctx->time_end(1);
     ctx->launches++;
   }

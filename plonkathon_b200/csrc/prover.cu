@@ -79,8 +79,9 @@ __global__ void k_perm_terms(const Fr* A, const Fr* B, const Fr* C, const Fr* S1
 
 // out[i] = num[i] / den[i] (inv(0) = 0), Montgomery's trick over the strided set {t, t+T, ...}
 // (strided so the accesses of a warp are coalesced).  num may be null (plain inversion).
+#define PB_BATCH_CH 16
 __global__ void __launch_bounds__(128) k_batch_div(const Fr* num, const Fr* den, Fr* out, uint64_t n, uint64_t T) {
-  const int CH = 8;
+  const int CH = PB_BATCH_CH;
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   Fr pref[CH];
@@ -297,7 +298,7 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
   {
     DevBuf den(n4 * 32);
     k_l0_num<<<PB_GRID(n4, 256), 0, st>>>(P->xs.as<Fr>(), n4, fr_from_u64(n), one, den.as<Fr>());
-    uint64_t T = (n4 + 7) / 8;
+    uint64_t T = (n4 + PB_BATCH_CH - 1) / PB_BATCH_CH;
     k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), P->l0_ext.as<Fr>(), n4, T);
     k_scale_by4<<<PB_GRID(n4, 256), 0, st>>>(P->l0_ext.as<Fr>(), n4, zh);
     ctx->launches += 3;
@@ -412,7 +413,7 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c) {
   k_perm_terms<<<PB_GRID(n, 128), 0, st>>>(P->lag[0].as<Fr>(), P->lag[1].as<Fr>(), P->lag[2].as<Fr>(),
                                           P->sel_lag[Prover::S1].as<Fr>(), P->sel_lag[Prover::S2].as<Fr>(),
                                           P->sel_lag[Prover::S3].as<Fr>(), P->roots.as<Fr>(), ch, n, num, den);
-  uint64_t T = (n + 7) / 8;
+  uint64_t T = (n + PB_BATCH_CH - 1) / PB_BATCH_CH;
   k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den, num, n, T);
   uint32_t n_tiles = (uint32_t)((n + PB_PROD_TILE - 1) / PB_PROD_TILE);
   PB_CHECK(n_tiles <= 65536, "group order too large for the product scan");
@@ -481,7 +482,7 @@ static void divide_linear(Prover* P, Fr* num, const Fr& point, Fr* den_buf) {
   cudaStream_t st = ctx->stream;
   ntt_run(ctx, num, num, P->log_n, false, n, P->gpow.as<Fr>(), nullptr);
   k_coset_minus<<<PB_GRID(n, 256), 0, st>>>(P->roots.as<Fr>(), P->g, point, n, den_buf);
-  uint64_t T = (n + 7) / 8;
+  uint64_t T = (n + PB_BATCH_CH - 1) / PB_BATCH_CH;
   k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den_buf, num, n, T);
   ctx->launches += 2;
   ntt_run(ctx, num, num, P->log_n, true, n, nullptr, P->ginv_pow.as<Fr>());

@@ -101,6 +101,9 @@ def test_curve_ops(lib):
                 bb = limbs(mont(b[0]) | (mont(b[1]) << 256), 2)
                 lib.hs_curve_op(0, acc, bb, 0, out)
                 assert to_affine(lib, out) == O.g1_add(a, b)
+                out_u = (ctypes.c_uint32 * 32)()
+                lib.hs_curve_op(4, acc, bb, 0, out_u)  # SIMT-uniform variant
+                assert to_affine(lib, out_u) == O.g1_add(a, b)
             lib.hs_curve_op(1, acc, xyzz(lib, b), 0, out)  # full add
             assert to_affine(lib, out) == O.g1_add(a, b)
         # chains with non-trivial ZZ: ((p+q)+q)+(p+q) etc.
