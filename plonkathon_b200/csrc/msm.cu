@@ -38,7 +38,10 @@ struct MsmGeom {
   uint32_t bucket_stride;   // generic: half ; fixed-base: 0
   uint64_t point_stride;    // generic: 0 ; fixed-base: n (index of window w's copy of point i = w*n + i)
   uint32_t nb;              // total buckets
+  uint32_t batch;           // fixed-base only: number of MSMs sharing the points (bucket set k at k * half)
 };
+
+struct ScalarBatch { const Fr* p[4]; };
 
 // ---- signed-digit walk shared by the histogram and scatter passes
 struct DigitWalk {
@@ -63,13 +66,14 @@ struct DigitWalk {
 };
 
 // counts[bucket]++ for every non-zero digit
-__global__ void k_msm_histogram(const Fr* scalars, uint64_t n, int from_mont, MsmGeom g, uint32_t* counts) {
+__global__ void k_msm_histogram(ScalarBatch sb, uint64_t n, int from_mont, MsmGeom g, uint32_t* counts) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  DigitWalk dw(scalars, i, from_mont);
+  const uint32_t k = blockIdx.y;
+  DigitWalk dw(sb.p[k], i, from_mont);
   for (uint32_t w = 0; w < g.W; w++) {
     uint32_t neg, d = dw.next(w, g, neg);
-    if (d) atomicAdd(&counts[w * g.bucket_stride + (d - 1)], 1u);
+    if (d) atomicAdd(&counts[k * g.half + w * g.bucket_stride + (d - 1)], 1u);
   }
 }
 
@@ -145,15 +149,16 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t* counts, uint32_t n
 }
 
 // sorted[offsets[key] + cursor++] = point index | sign << 31
-__global__ void k_msm_scatter(const Fr* scalars, uint64_t n, int from_mont, MsmGeom g, const uint32_t* offsets,
+__global__ void k_msm_scatter(ScalarBatch sb, uint64_t n, int from_mont, MsmGeom g, const uint32_t* offsets,
                               uint32_t* cursors, uint32_t* sorted) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  DigitWalk dw(scalars, i, from_mont);
+  const uint32_t k = blockIdx.y;
+  DigitWalk dw(sb.p[k], i, from_mont);
   for (uint32_t w = 0; w < g.W; w++) {
     uint32_t neg, d = dw.next(w, g, neg);
     if (d) {
-      uint32_t key = w * g.bucket_stride + (d - 1);
+      uint32_t key = k * g.half + w * g.bucket_stride + (d - 1);
       uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
       sorted[pos] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
     }
@@ -435,18 +440,25 @@ static void host_horner_to_affine(const std::vector<G1XYZZ>& ws, uint32_t c, uin
 }
 
 // points: Montgomery affine (generic: n points; fixed-base: expanded table W*n).
-void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
-             bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity) {
+// batch > 1 (fixed-base only): `batch` scalar vectors against the same points in one pass; the k-th MSM
+// uses bucket set k, which the reduction phase treats exactly like an extra window.
+void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* const* scalars, uint32_t batch,
+                   bool scalars_mont, uint32_t c, bool fixed_base, uint64_t point_stride, uint8_t* out_xy /*batch*64*/,
+                   int* is_identity /*batch*/) {
   PB_CHECK(n > 0, "empty MSM");
+  PB_CHECK(batch >= 1 && batch <= 4 && (fixed_base || batch == 1), "bad MSM batch");
   MsmGeom g;
   g.c = c;
   g.W = windows_for(c);
   g.half = 1u << (c - 1);
   g.bucket_stride = fixed_base ? 0 : g.half;
   g.point_stride = fixed_base ? point_stride : 0;
-  g.nb = fixed_base ? g.half : g.half * g.W;
+  g.nb = fixed_base ? g.half * batch : g.half * g.W;
+  g.batch = batch;
   PB_CHECK((fixed_base ? (uint64_t)g.W * point_stride : n) < (1ull << 31), "MSM too large for 31-bit point ids");
-  uint32_t n_windows_out = fixed_base ? 1 : g.W;
+  uint32_t n_windows_out = fixed_base ? batch : g.W;
+  ScalarBatch sb;
+  for (uint32_t k = 0; k < 4; k++) sb.p[k] = k < batch ? scalars[k] : nullptr;
 
   DevBuf& sorted = ctx->scratch[2];
   DevBuf& counts = ctx->scratch[3];
@@ -458,7 +470,7 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   uint32_t seg_len = 32;
   if (const char* e = getenv("PB200_MSM_SEG")) seg_len = (uint32_t)atoi(e);
   PB_CHECK(seg_len >= 1 && seg_len <= 4096, "bad PB200_MSM_SEG");
-  uint64_t entries = n * g.W;
+  uint64_t entries = n * g.W * batch;
   PB_CHECK(entries < (1ull << 32), "MSM too large (n * windows must fit 32 bits)");
   sorted.ensure(entries * 4);
   counts.ensure((size_t)g.nb * 4);
@@ -472,7 +484,7 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   cudaStream_t st = ctx->stream;
   PB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)g.nb * 4, st));
   unsigned blocks = (unsigned)((n + 127) / 128);
-  k_msm_histogram<<<blocks, 128, 0, st>>>(scalars, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
+  k_msm_histogram<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
   {
     uint32_t n_tiles = (g.nb + PB_SCAN_TILE - 1) / PB_SCAN_TILE;
     PB_CHECK(n_tiles <= 8192, "too many buckets for the scan");
@@ -482,8 +494,8 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
     k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums, offsets.as<uint32_t>());
     ctx->launches += 2;
   }
-  k_msm_scatter<<<blocks, 128, 0, st>>>(scalars, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
-                                        counts.as<uint32_t>(), sorted.as<uint32_t>());
+  k_msm_scatter<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
+                                                     counts.as<uint32_t>(), sorted.as<uint32_t>());
   // balanced accumulation over fixed segments of L sorted entries
   {
     const uint32_t L = seg_len;
@@ -525,7 +537,19 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
   std::vector<G1XYZZ> ws(n_windows_out);
   PB_CUDA(cudaMemcpyAsync(ws.data(), wsums.p, n_windows_out * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
-  host_horner_to_affine(ws, c, out_xy, is_identity);
+  if (fixed_base) {
+    for (uint32_t k = 0; k < batch; k++) {
+      std::vector<G1XYZZ> one(1, ws[k]);
+      host_horner_to_affine(one, c, out_xy + 64 * k, is_identity + k);
+    }
+  } else {
+    host_horner_to_affine(ws, c, out_xy, is_identity);
+  }
+}
+
+void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
+             bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity) {
+  msm_run_batch(ctx, points, n, &scalars, 1, scalars_mont, c, fixed_base, point_stride, out_xy, is_identity);
 }
 
 // ---- SRS --------------------------------------------------------------------------------
@@ -648,6 +672,18 @@ void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scala
   } else {
     msm_run(ctx, srs->base.as<G1Affine>(), m, d_scalars, scalars_mont, msm_default_window(m, false), false, 0, out_xy,
             is_identity);
+  }
+}
+
+// `batch` commitments (<= 4) to coefficient vectors of the same length m in one pass over the SRS
+void srs_msm_batch(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t m, bool scalars_mont,
+                   uint8_t* out_xy, int* is_identity) {
+  PB_CHECK(m <= srs->n, "Not enough powers in setup");
+  if (srs->expanded.p && batch > 1) {
+    msm_run_batch(ctx, srs->expanded.as<G1Affine>(), m, d_scalars, batch, scalars_mont, srs->c, true, srs->n, out_xy,
+                  is_identity);
+  } else {
+    for (uint32_t k = 0; k < batch; k++) srs_msm(ctx, srs, d_scalars[k], m, scalars_mont, out_xy + 64 * k, is_identity + k);
   }
 }
 

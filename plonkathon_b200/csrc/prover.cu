@@ -397,7 +397,8 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
   ntt_run(ctx, P->pi_lag.as<Fr>(), P->coeff[4].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
-  for (int k = 0; k < 3; k++) P->commit(P->coeff[k].as<Fr>(), n, P->proof.pts[k]);
+  const Fr* abc[3] = {P->coeff[0].as<Fr>(), P->coeff[1].as<Fr>(), P->coeff[2].as<Fr>()};
+  P->commit_batch(abc, 3, n, P->proof.pts[0]);
 }
 
 // ---- round 2 (prover.py:121-152) -------------------------------------------------------------------------
@@ -458,7 +459,8 @@ void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
   k_count_nonzero<<<PB_GRID(n, 256), 0, st>>>(P->tq.as<Fr>() + 3 * n, n, P->flags.as<uint32_t>());
   ctx->launches++;
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: quotient has degree >= 3n (prover.py:205-208)");
-  for (int k = 0; k < 3; k++) P->commit(P->tq.as<Fr>() + k * n, n, P->proof.pts[4 + k]);
+  const Fr* t123[3] = {P->tq.as<Fr>(), P->tq.as<Fr>() + n, P->tq.as<Fr>() + 2 * n};
+  P->commit_batch(t123, 3, n, P->proof.pts[4]);
 }
 
 // ---- round 4 (prover.py:228-239) -------------------------------------------------------------------------
@@ -553,8 +555,8 @@ void prover_round5(Prover* P, const Fr& v_c) {
   k_count_nonzero<<<1, 32, 0, st>>>(wzw + (n - 1), 1, P->flags.as<uint32_t>());
   ctx->launches += 2;
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: opening quotient has degree >= n-1 (prover.py:288,299)");
-  P->commit(wz, n, P->proof.pts[7]);
-  P->commit(wzw, n, P->proof.pts[8]);
+  const Fr* ws[2] = {wz, wzw};
+  P->commit_batch(ws, 2, n, P->proof.pts[7]);
 }
 
 // canonical 768-byte proof: Proof.flatten() order (prover.py:18-35), G1 as x||y, every integer 32-byte

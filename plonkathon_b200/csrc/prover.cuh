@@ -6,6 +6,8 @@ namespace pb200 {
 
 struct Srs;
 void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
+void srs_msm_batch(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t m, bool scalars_mont,
+                   uint8_t* out_xy, int* is_identity);
 
 struct Proof {
   uint8_t pts[9][64];    // a_1 b_1 c_1 z_1 t_lo t_mid t_hi W_z W_zw  (canonical LE x||y)
@@ -42,6 +44,13 @@ struct Prover {
 
   enum { QM = 0, QL, QR, QO, QC, S1, S2, S3 };
 
+  // several commitments in one pass over the SRS (out: count * 64 bytes, contiguous)
+  void commit_batch(const Fr* const* d_coeffs, uint32_t count, uint64_t m, uint8_t* out_xy) {
+    int ident[4] = {0, 0, 0, 0};
+    srs_msm_batch(ctx, srs, d_coeffs, count, m, true, out_xy, ident);
+    for (uint32_t k = 0; k < count; k++)
+      PB_CHECK(!ident[k], "commitment is the point at infinity (unsupported by the reference transcript)");
+  }
   void commit(const Fr* d_coeffs, uint64_t m, uint8_t* out_xy) {
     int ident = 0;
     srs_msm(ctx, srs, d_coeffs, m, true, out_xy, &ident);
