@@ -587,3 +587,91 @@ class Prover:
         Wzw = self.expanded_evals_to_coeffs(Wzw_b)
         assert Wzw[n:] == [0] * (3 * n)  # prover.py:299
         return (self.setup.commit(fft(Wz[:n])), self.setup.commit(fft(Wzw[:n])))
+
+
+# ----------------------------------------------------------------------------
+# Verification (TESTING_verifier_DO_NOT_OPEN.py:39-163 `verify_proof`), for structured test SRSs whose
+# toxic value tau is known: the single pairing equation e(X_2, A) == e(G2, B) holds iff tau * A == B in G1,
+# so the check needs no pairing.  Used as an independent end-to-end check of proofs at sizes (2^20 gates)
+# the reference itself cannot produce.  Validated against the pairing verifier on the golden circuits'
+# family in tests/test_oracle_pins.py.
+# ----------------------------------------------------------------------------
+def eval_lagrange_at(vals: Sequence[int], x: int) -> int:
+    """Value at x of the polynomial given by Lagrange values on the n-th roots of unity (barycentric form with
+    one batched inversion; x must not be a root of unity)."""
+    n = len(vals)
+    w = root_of_unity(n)
+    diffs, cur = [], 1
+    for _ in range(n):
+        diffs.append((x - cur) % R_MOD)
+        cur = cur * w % R_MOD
+    pref, run = [], 1
+    for d in diffs:
+        pref.append(run)
+        run = run * d % R_MOD
+    inv = pow(run, -1, R_MOD)
+    acc, cur_w = 0, pow(w, n - 1, R_MOD)
+    w_inv = pow(w, -1, R_MOD)
+    for i in range(n - 1, -1, -1):
+        di = inv * pref[i] % R_MOD
+        inv = inv * diffs[i] % R_MOD
+        if vals[i]:
+            acc += vals[i] * cur_w % R_MOD * di
+        cur_w = cur_w * w_inv % R_MOD
+    return (pow(x, n, R_MOD) - 1) * inv0(n, R_MOD) % R_MOD * (acc % R_MOD) % R_MOD
+
+
+def compute_challenges(proof: dict):
+    """TESTING_verifier_DO_NOT_OPEN.py:267-277."""
+    tr = Transcript(b"plonk")
+    beta, gamma = tr.round_1(proof["a_1"], proof["b_1"], proof["c_1"])
+    alpha, _cof = tr.round_2(proof["z_1"])
+    zeta = tr.round_3(proof["t_lo_1"], proof["t_mid_1"], proof["t_hi_1"])
+    v = tr.round_4(*[proof[k] for k in ("a_eval", "b_eval", "c_eval", "s1_eval", "s2_eval", "z_shifted_eval")])
+    u = tr.round_5(proof["W_z_1"], proof["W_zw_1"])
+    return beta, gamma, alpha, zeta, v, u
+
+
+def verify_proof_trapdoor(group_order: int, vk: dict, proof: dict, public: Sequence[int], tau: int) -> bool:
+    """TESTING_verifier_DO_NOT_OPEN.py:39-163 with the final pairing equation checked through tau.
+    vk: dict with G1 points Qm Ql Qr Qo Qc S1 S2 S3."""
+    n = group_order
+    beta, gamma, alpha, zeta, v, u = compute_challenges(proof)
+    w = root_of_unity(n)
+    ZH_ev = (pow(zeta, n, R_MOD) - 1) % R_MOD
+    L0_ev = ZH_ev * inv0(n * (zeta - 1), R_MOD) % R_MOD
+    # PI(zeta) = sum_i (-public_i) L_i(zeta),  L_i(zeta) = w^i (zeta^n - 1) / (n (zeta - w^i))
+    PI_ev = 0
+    for i, p in enumerate(public):
+        wi = pow(w, i, R_MOD)
+        PI_ev += (-p) * wi % R_MOD * ZH_ev % R_MOD * inv0(n * (zeta - wi), R_MOD)
+    PI_ev %= R_MOD
+    a, b, c = proof["a_eval"], proof["b_eval"], proof["c_eval"]
+    s1, s2, zw = proof["s1_eval"], proof["s2_eval"], proof["z_shifted_eval"]
+    r0 = (PI_ev - L0_ev * alpha * alpha
+          - alpha * (a + beta * s1 + gamma) * (b + beta * s2 + gamma) % R_MOD * (c + gamma) % R_MOD * zw) % R_MOD
+    D = ec_lincomb_naive([
+        (vk["Qm"], a * b), (vk["Ql"], a), (vk["Qr"], b), (vk["Qo"], c), (vk["Qc"], 1),
+        (proof["z_1"], ((a + beta * zeta + gamma) * (b + 2 * beta * zeta + gamma) % R_MOD
+                        * (c + 3 * beta * zeta + gamma) % R_MOD * alpha + L0_ev * alpha * alpha + u)),
+        (vk["S3"], -(a + beta * s1 + gamma) * (b + beta * s2 + gamma) % R_MOD * alpha * beta % R_MOD * zw),
+        (proof["t_lo_1"], -ZH_ev), (proof["t_mid_1"], -ZH_ev * pow(zeta, n, R_MOD)),
+        (proof["t_hi_1"], -ZH_ev * pow(zeta, 2 * n, R_MOD)),
+    ])
+    F = ec_lincomb_naive([(D, 1), (proof["a_1"], v), (proof["b_1"], pow(v, 2, R_MOD)),
+                          (proof["c_1"], pow(v, 3, R_MOD)), (vk["S1"], pow(v, 4, R_MOD)),
+                          (vk["S2"], pow(v, 5, R_MOD))])
+    E = g1_multiply(G1, (-r0 + v * a + v * v * b + pow(v, 3, R_MOD) * c + pow(v, 4, R_MOD) * s1
+                         + pow(v, 5, R_MOD) * s2 + u * zw) % R_MOD)
+    lhs = g1_multiply(ec_lincomb_naive([(proof["W_z_1"], 1), (proof["W_zw_1"], u)]), tau)
+    rhs = ec_lincomb_naive([(proof["W_z_1"], zeta), (proof["W_zw_1"], u * zeta % R_MOD * w),
+                            (F, 1), (E, -1)])
+    return lhs == rhs
+
+
+def proof_from_bytes(raw: bytes) -> dict:
+    w = [int.from_bytes(raw[i:i + 32], "big") for i in range(0, 768, 32)]
+    vals = [(w[0], w[1]), (w[2], w[3]), (w[4], w[5]), (w[6], w[7]), (w[8], w[9]), (w[10], w[11]), (w[12], w[13])]
+    vals += w[14:20]
+    vals += [(w[20], w[21]), (w[22], w[23])]
+    return dict(zip(PROOF_FIELDS, vals))

@@ -298,3 +298,43 @@ def test_prove_synthetic_vs_oracle(pb, log_n, fill):
     osetup = O.Setup([(p[0].n, p[1].n) for p in setup.powers_of_x], None)
     a, b, cc = c.wires_values()
     assert raw == O.proof_bytes(O.Prover(osetup, opk).prove(a, b, cc, c.public_values()))
+
+
+def test_prove_2p20_gates_verifies(pb):
+    """BASELINE.json's headline size: a 2^20-gate synthetic circuit.  The reference cannot produce a proof
+    at this size (5 h of Python; SRS file holds 2^11 powers), so parity is established end to end by the
+    reference's verification equation (TESTING_verifier_DO_NOT_OPEN.py:39-163) evaluated by the oracle with
+    the known tau of the structured SRS, plus independent CPU evaluation of two verification-key
+    commitments, plus determinism (two runs, host-buffer and device-buffer paths agree in bench.py)."""
+    from plonkathon_b200 import synthetic as syn
+    log_n = 20
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=7, n_public=2)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    prover = pb.Prover.from_arrays(setup, n, pk)
+    raw = prover.prove_arrays(A, B, C, public)
+    assert prover.prove_arrays(A, B, C, public) == raw
+    proof = O.proof_from_bytes(raw)
+    for k in ("a_1", "z_1", "t_hi_1", "W_zw_1"):
+        assert O.g1_is_on_curve(proof[k])
+
+    def commit(col):
+        import ctypes
+        from plonkathon_b200 import _lib
+        out = ctypes.create_string_buffer(64)
+        ident = ctypes.c_int()
+        _lib.check(_lib.lib().pb200_srs_commit_lagrange_host(
+            setup.ctx.handle, setup._srs, pk[col].ctypes.data_as(ctypes.c_void_p), log_n, out, ctypes.byref(ident)))
+        return None if ident.value else (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little"))
+
+    vk = {k: commit(col) for k, col in (("Qm", "QM"), ("Ql", "QL"), ("Qr", "QR"), ("Qo", "QO"), ("Qc", "QC"),
+                                        ("S1", "S1"), ("S2", "S2"), ("S3", "S3"))}
+    # two of the eight commitments re-derived on the CPU: [f(tau)] G with f evaluated from its Lagrange values
+    S1, _, _ = syn.permutation_polys(c.wire_L, c.wire_R, c.wire_O, n, c.n_constraints)
+    assert vk["S1"] == O.g1_multiply(O.G1, O.eval_lagrange_at(S1, TAU))
+    assert vk["Qm"] == O.g1_multiply(O.G1, O.eval_lagrange_at(c.QM, TAU))
+    assert O.verify_proof_trapdoor(n, vk, proof, public, TAU)
+    bad = dict(proof)
+    bad["z_shifted_eval"] = (bad["z_shifted_eval"] + 1) % R
+    assert not O.verify_proof_trapdoor(n, vk, bad, public, TAU)
