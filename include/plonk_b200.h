@@ -127,6 +127,18 @@ int pb200_prover_round3(pb200_prover* p, const uint8_t* alpha, const uint8_t* ff
 int pb200_prover_round4(pb200_prover* p, const uint8_t* zeta, uint8_t* h_evals /*6*32*/);             /* :228 */
 int pb200_prover_round5(pb200_prover* p, const uint8_t* v, uint8_t* h_w_xy /*2*64*/);                 /* :241 */
 
+/* ---- multi-GPU MSM join (one process per GPU; the collective itself is the caller's NCCL allgather) ---- */
+/* Restrict every commitment of this prover to the SRS powers [first, first+count) (point-range shard of
+ * setup.py:66-72's MSM).  While enabled, the rounds leave XYZZ partial sums (128 bytes each, Montgomery limbs)
+ * instead of affine points; slots follow the proof order a b c z t_lo t_mid t_hi W_z W_zw. */
+int pb200_prover_set_shard(pb200_prover* p, uint64_t first, uint64_t count, int enable);
+int pb200_prover_read_partials(pb200_prover* p, unsigned first_slot, unsigned count, uint8_t* h_xyzz);
+/* store combined commitments (canonical x||y little-endian) back into the proof, and serialise it */
+int pb200_prover_set_points(pb200_prover* p, unsigned first_slot, unsigned count, const uint8_t* h_xy);
+int pb200_prover_serialize(pb200_prover* p, uint8_t* h_proof768);
+/* sum `count` XYZZ partials gathered from all ranks into one canonical affine point (host arithmetic) */
+int pb200_g1_combine_partials_host(const uint8_t* h_xyzz, unsigned count, uint8_t* h_out_xy, int* is_identity);
+
 /* ---- Transcript (transcript.py:58-123; host code) ---------------------------------------------- */
 int pb200_transcript_create(const uint8_t* label, size_t label_len, pb200_transcript** out);
 void pb200_transcript_destroy(pb200_transcript* t);

@@ -65,6 +65,11 @@ def _load():
         "pb200_prover_round3": (I, [V, V, V, V]),
         "pb200_prover_round4": (I, [V, V, V]),
         "pb200_prover_round5": (I, [V, V, V]),
+        "pb200_prover_set_shard": (I, [V, U64, U64, I]),
+        "pb200_prover_read_partials": (I, [V, U, U, V]),
+        "pb200_prover_set_points": (I, [V, U, U, V]),
+        "pb200_prover_serialize": (I, [V, V]),
+        "pb200_g1_combine_partials_host": (I, [V, U, V, P(I)]),
         "pb200_transcript_create": (I, [V, ctypes.c_size_t, P(V)]),
         "pb200_transcript_destroy": (None, [V]),
         "pb200_transcript_append_message": (I, [V, V, ctypes.c_size_t, V, ctypes.c_size_t]),

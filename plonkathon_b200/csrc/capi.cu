@@ -41,6 +41,9 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c);
 void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c);
 void prover_round4(Prover* P, const Fr& zeta_c);
 void prover_round5(Prover* P, const Fr& v_c);
+void prover_set_shard(Prover* P, uint64_t first, uint64_t count, bool enable);
+void prover_serialize(const Prover* P, uint8_t* out768);
+void g1_combine_partials_host(const G1XYZZ* parts, uint32_t count, uint8_t* out_xy, int* is_identity);
 }  // namespace pb200
 
 using namespace pb200;
@@ -382,6 +385,36 @@ int pb200_prover_round5(pb200_prover* p, const uint8_t* v, uint8_t* h_w_xy) {
   Prover* P = reinterpret_cast<Prover*>(p);
   prover_round5(P, load_fr_canonical(v));
   memcpy(h_w_xy, P->proof.pts[7], 2 * 64);
+  PB_API_END
+}
+
+int pb200_prover_set_shard(pb200_prover* p, uint64_t first, uint64_t count, int enable) {
+  PB_API_BEGIN
+  prover_set_shard(reinterpret_cast<Prover*>(p), first, count, enable != 0);
+  PB_API_END
+}
+int pb200_prover_read_partials(pb200_prover* p, unsigned first_slot, unsigned count, uint8_t* h_xyzz) {
+  PB_API_BEGIN
+  PB_CHECK(first_slot + count <= 9, "proof has 9 commitment slots");
+  memcpy(h_xyzz, reinterpret_cast<Prover*>(p)->partials + first_slot, (size_t)count * sizeof(G1XYZZ));
+  PB_API_END
+}
+int pb200_prover_set_points(pb200_prover* p, unsigned first_slot, unsigned count, const uint8_t* h_xy) {
+  PB_API_BEGIN
+  PB_CHECK(first_slot + count <= 9, "proof has 9 commitment slots");
+  memcpy(reinterpret_cast<Prover*>(p)->proof.pts[first_slot], h_xy, (size_t)count * 64);
+  PB_API_END
+}
+int pb200_prover_serialize(pb200_prover* p, uint8_t* h_proof768) {
+  PB_API_BEGIN
+  prover_serialize(reinterpret_cast<Prover*>(p), h_proof768);
+  PB_API_END
+}
+int pb200_g1_combine_partials_host(const uint8_t* h_xyzz, unsigned count, uint8_t* h_out_xy, int* is_identity) {
+  PB_API_BEGIN
+  std::vector<G1XYZZ> parts(count);
+  memcpy(parts.data(), h_xyzz, (size_t)count * sizeof(G1XYZZ));
+  g1_combine_partials_host(parts.data(), count, h_out_xy, is_identity);
   PB_API_END
 }
 

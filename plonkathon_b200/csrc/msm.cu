@@ -444,7 +444,7 @@ static void host_horner_to_affine(const std::vector<G1XYZZ>& ws, uint32_t c, uin
 // uses bucket set k, which the reduction phase treats exactly like an extra window.
 void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* const* scalars, uint32_t batch,
                    bool scalars_mont, uint32_t c, bool fixed_base, uint64_t point_stride, uint8_t* out_xy /*batch*64*/,
-                   int* is_identity /*batch*/) {
+                   int* is_identity /*batch*/, G1XYZZ* raw_out /*optional: batch XYZZ sums instead of affine*/) {
   PB_CHECK(n > 0, "empty MSM");
   PB_CHECK(batch >= 1 && batch <= 4 && (fixed_base || batch == 1), "bad MSM batch");
   MsmGeom g;
@@ -537,7 +537,10 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   std::vector<G1XYZZ> ws(n_windows_out);
   PB_CUDA(cudaMemcpyAsync(ws.data(), wsums.p, n_windows_out * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
   PB_CUDA(cudaStreamSynchronize(st));
-  if (fixed_base) {
+  if (raw_out) {
+    PB_CHECK(fixed_base, "raw MSM output is only available in fixed-base mode");
+    for (uint32_t k = 0; k < batch; k++) raw_out[k] = ws[k];
+  } else if (fixed_base) {
     for (uint32_t k = 0; k < batch; k++) {
       std::vector<G1XYZZ> one(1, ws[k]);
       host_horner_to_affine(one, c, out_xy + 64 * k, is_identity + k);
@@ -549,7 +552,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
 
 void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
              bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity) {
-  msm_run_batch(ctx, points, n, &scalars, 1, scalars_mont, c, fixed_base, point_stride, out_xy, is_identity);
+  msm_run_batch(ctx, points, n, &scalars, 1, scalars_mont, c, fixed_base, point_stride, out_xy, is_identity, nullptr);
 }
 
 // ---- SRS --------------------------------------------------------------------------------
@@ -681,10 +684,33 @@ void srs_msm_batch(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t 
   PB_CHECK(m <= srs->n, "Not enough powers in setup");
   if (srs->expanded.p && batch > 1) {
     msm_run_batch(ctx, srs->expanded.as<G1Affine>(), m, d_scalars, batch, scalars_mont, srs->c, true, srs->n, out_xy,
-                  is_identity);
+                  is_identity, nullptr);
   } else {
     for (uint32_t k = 0; k < batch; k++) srs_msm(ctx, srs, d_scalars[k], m, scalars_mont, out_xy + 64 * k, is_identity + k);
   }
+}
+
+// Point-range shard of `batch` commitments: sum over i in [first, first + count) of scalars[k][i] * P_i,
+// returned as XYZZ partial sums (Montgomery) for the caller to exchange and combine (multi-GPU MSM join).
+void srs_msm_batch_partial(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t first,
+                           uint64_t count, bool scalars_mont, G1XYZZ* out) {
+  PB_CHECK(first + count <= srs->n, "Not enough powers in setup");
+  PB_CHECK(srs->expanded.p, "sharded commitments need the fixed-base table (precompute)");
+  const Fr* sh[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (uint32_t k = 0; k < batch; k++) sh[k] = d_scalars[k] + first;
+  if (count == 0) {
+    for (uint32_t k = 0; k < batch; k++) out[k] = G1XYZZ::identity();
+    return;
+  }
+  msm_run_batch(ctx, srs->expanded.as<G1Affine>() + first, count, sh, batch, scalars_mont, srs->c, true, srs->n, nullptr,
+                nullptr, out);
+}
+
+// sum of XYZZ partials -> canonical affine (host arithmetic; O(count) group operations)
+void g1_combine_partials_host(const G1XYZZ* parts, uint32_t count, uint8_t* out_xy, int* is_identity) {
+  std::vector<G1XYZZ> ws(1, G1XYZZ::identity());
+  for (uint32_t k = 0; k < count; k++) g1_add(ws[0], parts[k]);
+  host_horner_to_affine(ws, 1, out_xy, is_identity);
 }
 
 uint64_t srs_size(Srs* s) { return s->n; }

@@ -161,7 +161,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
+// One register-blocked round: the thread owns the 8 tile positions base + k * 2^t0 (k = 0..7; base has three
+// zero bits inserted at bit t0) of column c, runs the radix-2 DIT stages t0+s_first .. t0+2 on them in
+// registers and writes them back.  Stage t0+s pairs k with k + 2^s and uses w_{2^(t0+s+1)}^j with
+// j = (low t0 bits of base) + (k mod 2^s) * 2^t0.
+__device__ __forceinline__ void ntt_round8(uint4* s_lo, uint4* s_hi, const uint4* t_lo, const uint4* t_hi, uint32_t q,
+                                           uint32_t c, uint32_t t0, uint32_t s_first, uint32_t log_b,
+                                           uint32_t log_cc) {
+  const uint32_t low = q & ((1u << t0) - 1);
+  const uint32_t base = ((q >> t0) << (t0 + 3)) | low;
+  Fr x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = ld_planes(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c);
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    if ((uint32_t)s < s_first) continue;
+    const uint32_t st = t0 + s;
+#pragma unroll
+    for (int m = 0; m < (1 << s); m++) {
+      Fr tw;
+      const bool unit = (st == 0);
+      if (!unit) tw = ld_planes(t_lo, t_hi, (low + ((uint32_t)m << t0)) << (log_b - 1 - st));
+#pragma unroll
+      for (int h = 0; h < (4 >> s); h++) {
+        const int k = m + (h << (s + 1));
+        Fr v = x[k + (1 << s)];
+        if (!unit) v = fp_mul(v, tw);
+        Fr u = x[k];
+        x[k] = fp_add(u, v);
+        x[k + (1 << s)] = fp_sub(u, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) st_planes(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c, x[k]);
+}
+
+__global__ void __launch_bounds__(256, 2) k_ntt_pass(PassParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t B = 1u << p.log_b, CC = 1u << p.log_cc, TE = B << p.log_cc;
   uint4* s_lo = reinterpret_cast<uint4*>(smem_raw);
@@ -201,21 +237,37 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
   __syncthreads();          // also orders tid 0's barrier init before the waits below
   mbar_wait(bar, 0);        // twiddles have landed
 
-  // ---- in-tile DIT stages
-  for (uint32_t t = 0; t < p.log_b; t++) {
-    const uint32_t half = 1u << t;
-    for (uint32_t q = tid; q < (TE >> 1); q += nth) {
-      uint32_t c = q & (CC - 1), qq = q >> p.log_cc;
-      uint32_t j = qq & (half - 1), grp = qq >> t;
-      uint32_t i0 = (((grp << (t + 1)) + j) << p.log_cc) | c;
-      uint32_t i1 = i0 + (half << p.log_cc);
-      Fr u = ld_planes(s_lo, s_hi, i0);
-      Fr v = ld_planes(s_lo, s_hi, i1);
-      if (t > 0) v = fp_mul(v, ld_planes(t_lo, t_hi, j << (p.log_b - 1 - t)));
-      st_planes(s_lo, s_hi, i0, fp_add(u, v));
-      st_planes(s_lo, s_hi, i1, fp_sub(u, v));
+  if (p.log_b >= 3) {
+    // ---- register-blocked rounds of three stages; a final partial round covers log_b mod 3 stages
+    const uint32_t groups = TE >> 3;  // (B / 8) x CC threads' worth of work
+    uint32_t t0 = 0;
+    for (; t0 + 3 <= p.log_b; t0 += 3) {
+      for (uint32_t w = tid; w < groups; w += nth) ntt_round8(s_lo, s_hi, t_lo, t_hi, w >> p.log_cc, w & (CC - 1), t0, 0, p.log_b, p.log_cc);
+      __syncthreads();
     }
-    __syncthreads();
+    if (t0 < p.log_b) {
+      const uint32_t rem = p.log_b - t0;  // 1 or 2 stages left: run them as the tail of a group at log_b - 3
+      for (uint32_t w = tid; w < groups; w += nth)
+        ntt_round8(s_lo, s_hi, t_lo, t_hi, w >> p.log_cc, w & (CC - 1), p.log_b - 3, 3 - rem, p.log_b, p.log_cc);
+      __syncthreads();
+    }
+  } else {
+    // ---- tiny transforms: plain radix-2 stages in shared memory
+    for (uint32_t t = 0; t < p.log_b; t++) {
+      const uint32_t half = 1u << t;
+      for (uint32_t q = tid; q < (TE >> 1); q += nth) {
+        uint32_t c = q & (CC - 1), qq = q >> p.log_cc;
+        uint32_t j = qq & (half - 1), grp = qq >> t;
+        uint32_t i0 = (((grp << (t + 1)) + j) << p.log_cc) | c;
+        uint32_t i1 = i0 + (half << p.log_cc);
+        Fr u = ld_planes(s_lo, s_hi, i0);
+        Fr v = ld_planes(s_lo, s_hi, i1);
+        if (t > 0) v = fp_mul(v, ld_planes(t_lo, t_hi, j << (p.log_b - 1 - t)));
+        st_planes(s_lo, s_hi, i0, fp_add(u, v));
+        st_planes(s_lo, s_hi, i1, fp_sub(u, v));
+      }
+      __syncthreads();
+    }
   }
 
   // ---- store (batch index fastest)
@@ -246,8 +298,8 @@ struct NttPlan {
   std::vector<NttPass> passes;
 };
 
-static const int kMaxLogB = 10;   // 1024-point tiles
-static const int kLogCC = 1;      // 2 adjacent columns (64 B) per tile row
+static const int kMaxLogB = 11;    // up to 2048-point tiles
+static const int kTileLog = 11;    // aim for 2048 elements (64 KiB) per tile: CC = 2048 / B adjacent columns
 
 static size_t pass_smem_bytes(int log_b, int log_cc) {
   size_t B = (size_t)1 << log_b, TE = B << log_cc, TW = B > 1 ? B / 2 : 1;
@@ -303,7 +355,7 @@ static std::unique_ptr<NttPlan> build_plan(Context* ctx, int log_n, bool inverse
       // columns of length N1, stride C = N / N1; batch over adjacent columns
       uint64_t C = N / N1;
       batch = C;
-      ps.log_cc = (int)std::min<uint64_t>(kLogCC, lb[1] + lb[2]);
+      ps.log_cc = std::min(std::max(0, kTileLog - lb[0]), lb[1] + lb[2]);
       uint64_t CC = (uint64_t)1 << ps.log_cc;
       q.t_lo_count = (uint32_t)(C / CC);
       q.r_hi = 0; q.r_lo = CC; q.r_cs = 1; q.r_bs = C;
@@ -321,7 +373,7 @@ static std::unique_ptr<NttPlan> build_plan(Context* ctx, int log_n, bool inverse
       // within row k1 (length M = N2*N3): columns of length N2, stride N3
       uint64_t M = N2 * N3;
       batch = N3;
-      ps.log_cc = (int)std::min<uint64_t>(kLogCC, lb[2]);
+      ps.log_cc = std::min(std::max(0, kTileLog - lb[1]), lb[2]);
       uint64_t CC = (uint64_t)1 << ps.log_cc;
       q.t_lo_count = (uint32_t)(N3 / CC);
       q.r_hi = M; q.r_lo = CC; q.r_cs = 1; q.r_bs = N3;
@@ -339,7 +391,7 @@ static std::unique_ptr<NttPlan> build_plan(Context* ctx, int log_n, bool inverse
       // last pass: contiguous rows of length B; batch over adjacent k1; transposed store
       q.twg = nullptr;
       q.b_fastest_load = 1;
-      ps.log_cc = (int)std::min<uint64_t>(kLogCC, lb[0]);
+      ps.log_cc = std::min(std::max(0, kTileLog - lb[i]), lb[0]);
       uint64_t CC = (uint64_t)1 << ps.log_cc;
       if (npass == 2) {
         batch = N1;
@@ -409,7 +461,7 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
     ctx->time_begin(1);
-    k_ntt_pass<<<(unsigned)ps.tiles, 512, smem, ctx->stream>>>(q);
+    k_ntt_pass<<<(unsigned)ps.tiles, 256, smem, ctx->stream>>>(q);
     ctx->time_end(1);
     ctx->launches++;
   }

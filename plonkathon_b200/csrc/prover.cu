@@ -324,6 +324,13 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
 
 void prover_destroy(Prover* p) { delete p; }
 
+void prover_set_shard(Prover* P, uint64_t first, uint64_t count, bool enable) {
+  PB_CHECK(!enable || first + count <= P->n, "shard exceeds the group order");
+  P->sharded = enable;
+  P->shard_first = first;
+  P->shard_count = count;
+}
+
 static uint32_t read_flag(Prover* P, int idx) {
   uint32_t v;
   PB_CUDA(cudaMemcpyAsync(&v, P->flags.as<uint32_t>() + idx, 4, cudaMemcpyDeviceToHost, P->ctx->stream));

@@ -8,6 +8,8 @@ struct Srs;
 void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
 void srs_msm_batch(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t m, bool scalars_mont,
                    uint8_t* out_xy, int* is_identity);
+void srs_msm_batch_partial(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t first,
+                           uint64_t count, bool scalars_mont, G1XYZZ* out);
 
 struct Proof {
   uint8_t pts[9][64];    // a_1 b_1 c_1 z_1 t_lo t_mid t_hi W_z W_zw  (canonical LE x||y)
@@ -41,22 +43,27 @@ struct Prover {
   Fr ev[6];                                      // Montgomery evaluations (round 4)
   Fr pi_ev;
   Proof proof;
+  // multi-GPU: this rank commits only to SRS powers [shard_first, shard_first + shard_count)
+  bool sharded = false;
+  uint64_t shard_first = 0, shard_count = 0;
+  G1XYZZ partials[9];
 
   enum { QM = 0, QL, QR, QO, QC, S1, S2, S3 };
 
   // several commitments in one pass over the SRS (out: count * 64 bytes, contiguous)
   void commit_batch(const Fr* const* d_coeffs, uint32_t count, uint64_t m, uint8_t* out_xy) {
+    if (sharded) {
+      // point-range shard: leave XYZZ partial sums for the caller's allgather + combine (slot = index of out_xy)
+      size_t slot = (size_t)(out_xy - proof.pts[0]) / 64;
+      srs_msm_batch_partial(ctx, srs, d_coeffs, count, shard_first, shard_count, true, partials + slot);
+      return;
+    }
     int ident[4] = {0, 0, 0, 0};
     srs_msm_batch(ctx, srs, d_coeffs, count, m, true, out_xy, ident);
     for (uint32_t k = 0; k < count; k++)
       PB_CHECK(!ident[k], "commitment is the point at infinity (unsupported by the reference transcript)");
   }
-  void commit(const Fr* d_coeffs, uint64_t m, uint8_t* out_xy) {
-    int ident = 0;
-    srs_msm(ctx, srs, d_coeffs, m, true, out_xy, &ident);
-    // transcript.py:65-67 cannot absorb the identity (item[0] on None); mirror that as an error
-    PB_CHECK(!ident, "commitment is the point at infinity (unsupported by the reference transcript)");
-  }
+  void commit(const Fr* d_coeffs, uint64_t m, uint8_t* out_xy) { commit_batch(&d_coeffs, 1, m, out_xy); }
 };
 
 

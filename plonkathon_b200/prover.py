@@ -176,7 +176,7 @@ class Prover:
                 c.ctypes.data_as(ctypes.c_void_p), pub.ctypes.data_as(ctypes.c_void_p), pub.shape[0], out))
         except _lib.PlonkB200Error as e:
             _raise(e)
-        return Message1(*_pts(out.raw, 3))
+        return Message1(*self._commitments(0, 3, out.raw))
 
     @staticmethod
     def _le(x) -> bytes:
@@ -189,7 +189,7 @@ class Prover:
             _lib.check(_lib.lib().pb200_prover_round2(self._h, self._le(self.beta), self._le(self.gamma), out))
         except _lib.PlonkB200Error as e:
             _raise(e)
-        return Message2(*_pts(out.raw, 1))
+        return Message2(*self._commitments(3, 1, out.raw))
 
     def round_3(self) -> Message3:
         """prover.py:154-226."""
@@ -198,7 +198,7 @@ class Prover:
             _lib.check(_lib.lib().pb200_prover_round3(self._h, self._le(self.alpha), self._le(self.fft_cofactor), out))
         except _lib.PlonkB200Error as e:
             _raise(e)
-        return Message3(*_pts(out.raw, 3))
+        return Message3(*self._commitments(4, 3, out.raw))
 
     def round_4(self) -> Message4:
         """prover.py:228-239."""
@@ -213,7 +213,11 @@ class Prover:
             _lib.check(_lib.lib().pb200_prover_round5(self._h, self._le(self.v), out))
         except _lib.PlonkB200Error as e:
             _raise(e)
-        return Message5(*_pts(out.raw, 2))
+        return Message5(*self._commitments(7, 2, out.raw))
+
+    def _commitments(self, first_slot: int, count: int, raw: bytes):
+        """commitments a round produced (overridden by the multi-GPU prover, which gathers partial sums)"""
+        return _pts(raw, count)
 
     def rlc(self, term_1, term_2):
         """prover.py:314-315."""
