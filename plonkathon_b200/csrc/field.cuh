@@ -227,8 +227,47 @@ PB_HD void fp_cios_step(uint32_t* U, uint32_t* V, uint32_t& w, const uint32_t* a
   V[7] = addc(V[7], 0u);
 }
 
+#if !defined(__CUDA_ARCH__) && defined(PB_HOST_FAST_MUL)
+// Host-only shortcut used by the library's own host code (final Horner / inversion of a commitment,
+// transcript challenge reduction): 4 x 64-bit CIOS with unsigned __int128.  Same function value as the limb
+// code below; the CPU unit tests build WITHOUT this macro so they exercise the device algorithm.
+template <class P>
+inline Fp<P> fp_mul_host64(const Fp<P>& a, const Fp<P>& b) {
+  typedef unsigned __int128 u128;
+  uint64_t A[4], B[4], M[4], T[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    A[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+    B[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+    M[i] = (uint64_t)P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32);
+  }
+  uint64_t np = 1;  // -p^-1 mod 2^64 by Newton iteration from the 32-bit constant's defining property
+  for (int k = 0; k < 6; k++) np *= 2 - M[0] * np;
+  np = (uint64_t)0 - np;
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) { c += (u128)A[j] * B[i] + T[j]; T[j] = (uint64_t)c; c >>= 64; }
+    c += T[4]; T[4] = (uint64_t)c; T[5] = (uint64_t)(c >> 64);
+    uint64_t m = T[0] * np;
+    c = (u128)m * M[0] + T[0]; c >>= 64;
+    for (int j = 1; j < 4; j++) { c += (u128)m * M[j] + T[j]; T[j - 1] = (uint64_t)c; c >>= 64; }
+    c += T[4]; T[3] = (uint64_t)c; T[4] = T[5] + (uint64_t)(c >> 64); T[5] = 0;
+  }
+  // T < 2p: one conditional subtraction
+  uint64_t r[4]; u128 br = 0; bool ge = T[4] != 0;
+  if (!ge) { ge = true; for (int i = 3; i >= 0; i--) { if (T[i] != M[i]) { ge = T[i] > M[i]; break; } } }
+  if (ge) { for (int i = 0; i < 4; i++) { u128 d = (u128)T[i] - M[i] - (uint64_t)br; r[i] = (uint64_t)d; br = (d >> 64) & 1; } }
+  else { for (int i = 0; i < 4; i++) r[i] = T[i]; }
+  Fp<P> o;
+  for (int i = 0; i < 4; i++) { o.v[2 * i] = (uint32_t)r[i]; o.v[2 * i + 1] = (uint32_t)(r[i] >> 32); }
+  return o;
+}
+#endif
+
 template <class P>
 PB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if !defined(__CUDA_ARCH__) && defined(PB_HOST_FAST_MUL)
+  return fp_mul_host64(a, b);
+#else
   uint32_t X[8], Y[8], w;
   fp_cios_step<P, true>(X, Y, w, a.v, b.v[0]);
   fp_cios_step<P, false>(Y, X, w, a.v, b.v[1]);
@@ -247,6 +286,7 @@ PB_HD Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
   r.v[7] = addc(X[7], 0u);
   fp_reduce_once(r);
   return r;
+#endif
 }
 
 template <class P>
@@ -254,6 +294,10 @@ PB_HD Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul(a, a); }
 
 template <class P>
 PB_HD Fp<P> fp_to_mont(const Fp<P>& a) { return fp_mul(a, Fp<P>::r2()); }
+
+// to_mont for an arbitrary 256-bit input (not necessarily < p): CIOS only needs one operand below p
+template <class P>
+PB_HD Fp<P> fp_to_mont_any(const Fp<P>& a) { return fp_mul(Fp<P>::r2(), a); }
 
 template <class P>
 PB_HD Fp<P> fp_from_mont(const Fp<P>& a) {

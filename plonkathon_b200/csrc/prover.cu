@@ -166,6 +166,81 @@ __global__ void __launch_bounds__(256) k_prod_apply(const Fr* f, uint64_t n, con
   }
 }
 
+// ---- division by (X - z) in coefficient space ---------------------------------------------------------------
+// q_(k-1) = s_k with s_k = N_k + z s_(k+1); multiplying through by z^k turns the recurrence into a plain suffix
+// sum: s_k z^k = sum_(m >= k) N_m z^m.  So: u = N .* z^m, suffix-sum scan (additions only), multiply by z^-k.
+#define PB_SUM_TILE 2048
+__device__ __forceinline__ Fr block_exclusive_sum_256(const Fr& v, Fr* sh, Fr* total) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    Fr x = sh[threadIdx.x];
+    Fr y = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : Fr::zero();
+    __syncthreads();
+    if ((int)threadIdx.x >= d) sh[threadIdx.x] = fp_add(x, y);
+    __syncthreads();
+  }
+  Fr excl = threadIdx.x ? sh[threadIdx.x - 1] : Fr::zero();
+  *total = sh[255];
+  __syncthreads();
+  return excl;
+}
+// all three kernels walk the vector from the top: logical position i <-> index n-1-i
+__global__ void __launch_bounds__(256) k_sufsum_tiles(const Fr* N, const Fr* zpow, uint64_t n, Fr* tile_sum) {
+  __shared__ Fr sh[256];
+  uint64_t base = (uint64_t)blockIdx.x * PB_SUM_TILE + threadIdx.x * 8;
+  Fr p = Fr::zero();
+  for (int k = 0; k < 8; k++)
+    if (base + k < n) { uint64_t m = n - 1 - (base + k); p = fp_add(p, fp_mul(ldg_fr(N + m), ldg_fr(zpow + m))); }
+  Fr total;
+  block_exclusive_sum_256(p, sh, &total);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_sufsum_scan_tiles(Fr* tile_sum, uint32_t n_tiles, Fr* total_out) {
+  __shared__ Fr sh[256];
+  uint32_t per = (n_tiles + 255) / 256;
+  uint32_t lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
+  Fr p = Fr::zero();
+  for (uint32_t i = lo; i < hi; i++) p = fp_add(p, tile_sum[i]);
+  Fr total;
+  Fr run = block_exclusive_sum_256(p, sh, &total);
+  for (uint32_t i = lo; i < hi; i++) {
+    Fr c = tile_sum[i];
+    tile_sum[i] = run;
+    run = fp_add(run, c);
+  }
+  if (threadIdx.x == 0) *total_out = total;
+}
+// out[m-1] = z^-m * sum_(m' >= m) N_m' z^m'  for m >= 1 ; out[n-1] = 0 ; the m = 0 sum (== N(z)) is dropped
+__global__ void __launch_bounds__(256) k_sufsum_apply(const Fr* N, const Fr* zpow, const Fr* zinvpow, uint64_t n,
+                                                      const Fr* tile_sum, Fr* out) {
+  __shared__ Fr sh[256];
+  uint64_t base = (uint64_t)blockIdx.x * PB_SUM_TILE + threadIdx.x * 8;
+  Fr c[8];
+  Fr p = Fr::zero();
+  for (int k = 0; k < 8; k++) {
+    if (base + k < n) { uint64_t m = n - 1 - (base + k); c[k] = fp_mul(ldg_fr(N + m), ldg_fr(zpow + m)); }
+    else c[k] = Fr::zero();
+    p = fp_add(p, c[k]);
+  }
+  Fr total;
+  Fr run = fp_add(tile_sum[blockIdx.x], block_exclusive_sum_256(p, sh, &total));
+  for (int k = 0; k < 8; k++) {
+    run = fp_add(run, c[k]);  // inclusive suffix sum at m
+    if (base + k < n) {
+      uint64_t m = n - 1 - (base + k);
+      if (m >= 1) out[m - 1] = fp_mul(run, ldg_fr(zinvpow + m));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = Fr::zero();
+}
+
+// basis_i[j] = w^i * (x_j^n - 1) / (n (x_j - w^i)) : the i-th Lagrange basis polynomial on the coset
+__global__ void k_lagrange_den(const Fr* X, uint64_t n4, Fr wi, Fr n_mont, Fr* den) {
+  uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n4) den[j] = fp_mul(n_mont, fp_sub(ldg_fr(X + j), wi));
+}
+
 // ---- round 3: quotient on the fixed coset -----------------------------------------------------------------
 struct QuotientArgs {
   const Fr *A, *B, *C, *Z, *PI;                       // extended (4n)
@@ -174,6 +249,10 @@ struct QuotientArgs {
   Fr zh_inv[4];                                       // 1 / (x_j^n - 1) for j mod 4
   Fr alpha, alpha2, beta, gamma, one;
   uint64_t n4;
+  // public inputs: PI(x_j) = sum_i pi_coef[i] * pi_basis[i][j]  (pi_cnt > 0), else the extended vector PI
+  int pi_cnt;
+  const Fr* pi_basis[8];
+  Fr pi_coef[8];
 };
 __global__ void __launch_bounds__(128) k_quotient(QuotientArgs q, Fr* T) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,7 +263,13 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs q, Fr* T) {
   gate = fp_add(gate, fp_mul(b, ldg_fr(q.QR + j)));
   gate = fp_add(gate, fp_mul(fp_mul(a, b), ldg_fr(q.QM + j)));
   gate = fp_add(gate, fp_mul(c, ldg_fr(q.QO + j)));
-  gate = fp_add(gate, fp_add(ldg_fr(q.PI + j), ldg_fr(q.QC + j)));
+  Fr pi = Fr::zero();
+  if (q.pi_cnt > 0) {
+    for (int i = 0; i < q.pi_cnt; i++) pi = fp_add(pi, fp_mul(q.pi_coef[i], ldg_fr(q.pi_basis[i] + j)));
+  } else if (q.PI) {
+    pi = ldg_fr(q.PI + j);
+  }
+  gate = fp_add(gate, fp_add(pi, ldg_fr(q.QC + j)));
   Fr ag = fp_add(a, q.gamma), bg = fp_add(b, q.gamma), cg = fp_add(c, q.gamma);
   Fr bx = fp_mul(q.beta, ldg_fr(q.X + j));
   Fr bx2 = fp_dbl(bx), bx3 = fp_add(bx2, bx);
@@ -315,7 +400,7 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
   for (int k = 0; k < 5; k++) { P->coeff[k].alloc(n * 32); P->ext[k].alloc(n4 * 32); }
   P->pi_lag.alloc(n * 32);
   P->tq.alloc(n4 * 32);
-  for (int k = 0; k < 4; k++) P->tmp[k].alloc(n * 32);
+  for (int k = 0; k < 5; k++) P->tmp[k].alloc(n * 32);
   P->flags.alloc(64);
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CUDA(cudaGetLastError());
@@ -374,6 +459,31 @@ static void store_canonical(uint8_t* dst, const Fr& mont) {
   memcpy(dst, c.v, 32);
 }
 
+// cached per prover: basis_i[j] = L_i(x_j) on the fixed coset for the first `count` rows
+static void ensure_pi_basis(Prover* P, int count) {
+  Context* ctx = P->ctx;
+  const uint64_t n = P->n, n4 = 4 * n;
+  cudaStream_t st = ctx->stream;
+  if ((int)P->pi_basis.size() >= count) return;
+  Fr w = fr_root_of_unity(P->log_n);
+  Fr gn = fp_pow_u64(P->g, n), i4 = fp_pow_u64(fr_root_of_unity(P->log_n + 2), n), one = Fr::one();
+  DevBuf den(n4 * 32);
+  for (int i = (int)P->pi_basis.size(); i < count; i++) {
+    Fr wi = fp_pow_u64(w, (uint64_t)i);
+    Four zh;  // w^i (x_j^n - 1): four values
+    Fr cur = gn;
+    for (int k = 0; k < 4; k++) { zh.v[k] = fp_mul(wi, fp_sub(cur, one)); cur = fp_mul(cur, i4); }
+    P->pi_basis.emplace_back(n4 * 32);
+    Fr* out = P->pi_basis.back().as<Fr>();
+    k_lagrange_den<<<PB_GRID(n4, 256), 0, st>>>(P->xs.as<Fr>(), n4, wi, fr_from_u64(n), den.as<Fr>());
+    uint64_t T = (n4 + PB_BATCH_CH - 1) / PB_BATCH_CH;
+    k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), out, n4, T);
+    k_scale_by4<<<PB_GRID(n4, 256), 0, st>>>(out, n4, zh);
+    ctx->launches += 3;
+  }
+  PB_CUDA(cudaStreamSynchronize(st));
+}
+
 // ---- round 1 (prover.py:86-119) -------------------------------------------------------------------------
 void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
                    uint64_t n_public, bool wires_on_device) {
@@ -402,7 +512,21 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
   ctx->launches++;
   for (int k = 0; k < 3; k++)
     ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
-  ntt_run(ctx, P->pi_lag.as<Fr>(), P->coeff[4].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  // public inputs: few of them -> PI is a short combination of cached Lagrange-basis vectors (no transforms);
+  // otherwise fall back to interpolating PI like any other column
+  P->n_public = n_public;
+  P->pi_sparse = n_public <= 8;
+  if (P->pi_sparse) {
+    ensure_pi_basis(P, (int)n_public);
+    P->pub_neg.resize(n_public);
+    for (uint64_t i = 0; i < n_public; i++) {
+      Fr v;
+      memcpy(v.v, h_public + 32 * i, 32);
+      P->pub_neg[i] = fp_neg(fp_to_mont(v));
+    }
+  } else {
+    ntt_run(ctx, P->pi_lag.as<Fr>(), P->coeff[4].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  }
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
   const Fr* abc[3] = {P->coeff[0].as<Fr>(), P->coeff[1].as<Fr>(), P->coeff[2].as<Fr>()};
   P->commit_batch(abc, 3, n, P->proof.pts[0]);
@@ -446,11 +570,13 @@ void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
   cudaStream_t st = ctx->stream;
   P->alpha = fp_to_mont(alpha_c);
   P->fft_cofactor = fp_to_mont(cofactor_c);
-  for (int k = 0; k < 5; k++)
+  for (int k = 0; k < (P->pi_sparse ? 4 : 5); k++)
     ntt_run(ctx, P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->log_n + 2, false, n, P->gpow.as<Fr>(), nullptr);
   QuotientArgs q;
+  q.pi_cnt = P->pi_sparse ? (int)P->n_public : 0;
+  for (int i = 0; i < q.pi_cnt; i++) { q.pi_basis[i] = P->pi_basis[i].as<Fr>(); q.pi_coef[i] = P->pub_neg[i]; }
   q.A = P->ext[0].as<Fr>(); q.B = P->ext[1].as<Fr>(); q.C = P->ext[2].as<Fr>(); q.Z = P->ext[3].as<Fr>();
-  q.PI = P->ext[4].as<Fr>();
+  q.PI = P->pi_sparse ? nullptr : P->ext[4].as<Fr>();
   q.QM = P->sel_ext[Prover::QM].as<Fr>(); q.QL = P->sel_ext[Prover::QL].as<Fr>(); q.QR = P->sel_ext[Prover::QR].as<Fr>();
   q.QO = P->sel_ext[Prover::QO].as<Fr>(); q.QC = P->sel_ext[Prover::QC].as<Fr>();
   q.S1 = P->sel_ext[Prover::S1].as<Fr>(); q.S2 = P->sel_ext[Prover::S2].as<Fr>(); q.S3 = P->sel_ext[Prover::S3].as<Fr>();
@@ -479,22 +605,52 @@ void prover_round4(Prover* P, const Fr& zeta_c) {
                         P->coeff[3].as<Fr>(), P->coeff[4].as<Fr>()};
   Fr xs[7] = {P->zeta, P->zeta, P->zeta, P->zeta, P->zeta, zw, P->zeta};
   Fr out[7];
-  eval_polys(P, 7, polys, xs, out);
+  eval_polys(P, P->pi_sparse ? 6 : 7, polys, xs, out);
   for (int k = 0; k < 6; k++) { P->ev[k] = out[k]; store_canonical(P->proof.evals[k], out[k]); }
-  P->pi_ev = out[6];
+  if (P->pi_sparse) {
+    // PI(zeta) = sum_i (-pub_i) w^i (zeta^n - 1) / (n (zeta - w^i)), one shared inversion (host arithmetic)
+    const uint64_t n = P->n;
+    Fr w = fr_root_of_unity(P->log_n), wi = Fr::one(), one = Fr::one();
+    Fr zh = fp_sub(fp_pow_u64(P->zeta, n), one), nm = fr_from_u64(n);
+    std::vector<Fr> den(P->n_public), pref(P->n_public), wis(P->n_public);
+    Fr run = one;
+    for (uint64_t i = 0; i < P->n_public; i++) {
+      den[i] = fp_mul(nm, fp_sub(P->zeta, wi));
+      wis[i] = wi;
+      pref[i] = run;
+      run = fp_mul(run, den[i]);
+      wi = fp_mul(wi, w);
+    }
+    Fr inv = fp_inv(run), acc = Fr::zero();
+    for (uint64_t i = P->n_public; i-- > 0;) {
+      Fr di = fp_mul(inv, pref[i]);
+      inv = fp_mul(inv, den[i]);
+      acc = fp_add(acc, fp_mul(fp_mul(P->pub_neg[i], wis[i]), di));
+    }
+    P->pi_ev = fp_mul(acc, zh);
+  } else {
+    P->pi_ev = out[6];
+  }
 }
 
-// (num coefficients, n) / (X - point) -> quotient coefficients in place (n-point coset division)
-static void divide_linear(Prover* P, Fr* num, const Fr& point, Fr* den_buf) {
+// (num coefficients, n) / (X - point) -> quotient coefficients (out != num), remainder dropped.
+// Coefficient-space synthetic division as a weighted suffix sum (see k_sufsum_*).
+static void divide_linear(Prover* P, const Fr* num, Fr* out, const Fr& point, Fr* pow_buf, Fr* invpow_buf) {
   Context* ctx = P->ctx;
   const uint64_t n = P->n;
   cudaStream_t st = ctx->stream;
-  ntt_run(ctx, num, num, P->log_n, false, n, P->gpow.as<Fr>(), nullptr);
-  k_coset_minus<<<PB_GRID(n, 256), 0, st>>>(P->roots.as<Fr>(), P->g, point, n, den_buf);
-  uint64_t T = (n + PB_BATCH_CH - 1) / PB_BATCH_CH;
-  k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den_buf, num, n, T);
-  ctx->launches += 2;
-  ntt_run(ctx, num, num, P->log_n, true, n, nullptr, P->ginv_pow.as<Fr>());
+  launch_powers(ctx, pow_buf, n, point, Fr::one());
+  launch_powers(ctx, invpow_buf, n, fp_inv(point), Fr::one());
+  uint32_t n_tiles = (uint32_t)((n + PB_SUM_TILE - 1) / PB_SUM_TILE);
+  ctx->scratch[0].ensure((size_t)(n_tiles + 1) * 32);
+  Fr* tiles = ctx->scratch[0].as<Fr>();
+  k_sufsum_tiles<<<n_tiles, 256, 0, st>>>(num, pow_buf, n, tiles);
+  k_sufsum_scan_tiles<<<1, 256, 0, st>>>(tiles, n_tiles, tiles + n_tiles);
+  k_sufsum_apply<<<n_tiles, 256, 0, st>>>(num, pow_buf, invpow_buf, n, tiles, out);
+  // the grand total is the remainder num(point); it must vanish (prover.py:267 R(zeta) == 0 and the degree
+  // asserts of prover.py:288,299 are equivalent to exact divisibility)
+  k_count_nonzero<<<1, 32, 0, st>>>(tiles + n_tiles, 1, P->flags.as<uint32_t>());
+  ctx->launches += 4;
 }
 
 // ---- round 5 (prover.py:241-306) -------------------------------------------------------------------------
@@ -546,23 +702,22 @@ void prover_round5(Prover* P, const Fr& v_c) {
   c0 = fp_sub(c0, fp_mul(v5, s2));
   L.c0 = c0;
   Fr* wz = P->tmp[0].as<Fr>();
+  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
   k_lincomb<<<PB_GRID(n, 128), 0, st>>>(L, wz);
   ctx->launches++;
-  divide_linear(P, wz, zeta, P->tmp[2].as<Fr>());
+  Fr* wz_q = P->tmp[1].as<Fr>();
+  divide_linear(P, wz, wz_q, zeta, P->tmp[2].as<Fr>(), P->tmp[3].as<Fr>());
   // W_zw numerator = Z - z_shifted_eval
   LinCombArgs M;
   M.vec[0] = P->coeff[3].as<Fr>(); M.w[0] = one; M.count = 1; M.n = n; M.c0 = fp_neg(zw);
-  Fr* wzw = P->tmp[1].as<Fr>();
+  Fr* wzw = P->tmp[0].as<Fr>();  // the W_z numerator is no longer needed
   k_lincomb<<<PB_GRID(n, 128), 0, st>>>(M, wzw);
   ctx->launches++;
-  divide_linear(P, wzw, fp_mul(zeta, fr_root_of_unity(P->log_n)), P->tmp[2].as<Fr>());
-  // both quotients have degree <= n-2: the top coefficient must vanish (prover.py:288,299)
-  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
-  k_count_nonzero<<<1, 32, 0, st>>>(wz + (n - 1), 1, P->flags.as<uint32_t>());
-  k_count_nonzero<<<1, 32, 0, st>>>(wzw + (n - 1), 1, P->flags.as<uint32_t>());
-  ctx->launches += 2;
-  PB_CHECK(read_flag(P, 0) == 0, "AssertionError: opening quotient has degree >= n-1 (prover.py:288,299)");
-  const Fr* ws[2] = {wz, wzw};
+  Fr* wzw_q = P->tmp[4].as<Fr>();
+  divide_linear(P, wzw, wzw_q, fp_mul(zeta, fr_root_of_unity(P->log_n)), P->tmp[2].as<Fr>(), P->tmp[3].as<Fr>());
+  PB_CHECK(read_flag(P, 0) == 0,
+           "AssertionError: opening numerator is not divisible by (X - point) (prover.py:267,288,299)");
+  const Fr* ws[2] = {wz_q, wzw_q};
   P->commit_batch(ws, 2, n, P->proof.pts[7]);
 }
 

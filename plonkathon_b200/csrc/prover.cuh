@@ -37,11 +37,16 @@ struct Prover {
   DevBuf pi_lag;
   DevBuf ext[5];         // A B C Z PI on the coset
   DevBuf tq;             // quotient evaluations / coefficients (4n)
-  DevBuf tmp[4];
+  DevBuf tmp[5];
   DevBuf flags;
   Fr beta, gamma, alpha, fft_cofactor, zeta, v;   // Montgomery
   Fr ev[6];                                      // Montgomery evaluations (round 4)
   Fr pi_ev;
+  // public inputs: when there are at most 8, PI is a combination of cached Lagrange-basis coset vectors
+  uint64_t n_public = 0;
+  bool pi_sparse = false;
+  std::vector<DevBuf> pi_basis;   // L_i on the fixed coset (4n each), i < 8
+  std::vector<Fr> pub_neg;        // -public_i, Montgomery (host)
   Proof proof;
   // multi-GPU: this rank commits only to SRS powers [shard_first, shard_first + shard_count)
   bool sharded = false;

@@ -146,12 +146,24 @@ class Transcript {
       }
     }
   }
-  // big-endian byte string mod r, canonical form (Horner over bytes with host limb arithmetic)
+  // big-endian byte string mod r, canonical form: Horner over 32-byte chunks, acc <- acc * 2^256 + chunk,
+  // where multiplying by 2^256 is exactly a conversion to Montgomery form (R = 2^256)
   static Fr reduce_be(const uint8_t* b, size_t n) {
-    Fr acc = Fr::zero();  // Montgomery accumulator
-    Fr c256 = fp_to_mont(small(256));
-    for (size_t i = 0; i < n; i++) acc = fp_add(fp_mul(acc, c256), fp_to_mont(small(b[i])));
-    return fp_from_mont(acc);
+    Fr acc = Fr::zero();
+    size_t pos = 0, first = n % 32 ? n % 32 : 32;
+    while (pos < n) {
+      size_t len = pos == 0 ? first : 32;
+      Fr chunk = Fr::zero();  // up to 256 bits, may exceed r: fold the top bits first
+      for (size_t k = 0; k < len; k++) {
+        size_t bit = 8 * (len - 1 - k);
+        chunk.v[bit >> 5] |= (uint32_t)b[pos + k] << (bit & 31);
+      }
+      // chunk < 2^256 < 6r: bring it below r with the Montgomery round trip (to_mont then from_mont reduce fully)
+      chunk = fp_from_mont(fp_to_mont_any(chunk));
+      acc = fp_add(fp_to_mont(acc), chunk);
+      pos += len;
+    }
+    return acc;
   }
 
  private:

@@ -63,3 +63,28 @@ def test_host_side_objects():
     assert [v.n for v in pb.Polynomial([S(1), S(2), S(3), S(4)], pb.Basis.LAGRANGE).shift(1).values] == [2, 3, 4, 1]
     with pytest.raises(ValueError):
         pb.ec_lincomb([])
+
+
+def test_transcript_is_host_code_and_matches_vectors():
+    """The Merlin transcript inside the .so needs no GPU: check it here against Merlin's conformance vector,
+    the reference-generated challenge fixture and the oracle's restatement on random schedules."""
+    import json
+    import random
+    import plonkathon_b200 as pb
+    from oracle import plonk_oracle as O
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "circuits.json")))
+    t = pb.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == g["merlin_vector"]
+    tr = pb.Transcript(b"plonk")
+    tr.append_point(b"a_1", (pb.FQ(1), pb.FQ(2)))
+    tr.append_scalar(b"a_eval", pb.Scalar(12345))
+    assert tr.get_and_append_challenge(b"beta") == int(g["transcript"]["beta"])
+    assert tr.get_and_append_challenge(b"gamma") == int(g["transcript"]["gamma"])
+    rng = random.Random(4)
+    a, b = pb.Transcript(b"plonk"), O.Transcript(b"plonk")
+    for i in range(40):
+        v = rng.randrange(O.R_MOD)
+        a.append_scalar(b"s%d" % i, pb.Scalar(v))
+        b.append_scalar(b"s%d" % i, v)
+        assert a.get_and_append_challenge(b"c").n == b.get_and_append_challenge(b"c")
