@@ -11,7 +11,7 @@ A "step" is one full proof (Prover.prove rounds 1-5, 9 KZG commitments) of a syn
   e2e   : proofs/s through the reference-facing C ABI call with HOST buffers (pb200_prover_prove): the three
           wire-value vectors are copied host->device from pinned memory and the 768-byte proof is read back
           inside the timed region, every step.
-N > 1: one process per GPU (torchrun), every rank proves its own instance of the circuit (proofs are
+N > 1: one process per GPU (torchrun), every rank proves its own copy of the circuit (proofs are
 independent units: no data-path collective); value = N*K proofs / max-over-ranks time ("weak")."""
 import argparse
 import ctypes
@@ -87,8 +87,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * scale * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u256 (BN254 Fr/Fq integers)", "data": "synthetic",
-        "config": {"workload": "PLONK prove, synthetic 2^%d-gate circuit, structured test SRS" % args.log_n,
-                   "log_n": args.log_n, "cpu_sample_log_n": args.cpu_log_n},
+        "config": {"workload": "PLONK prove (rounds 1-5, 9 KZG commits), synthetic 2^%d-gate circuit, structured "
+                               "test SRS [tau^i]G of 2^%d powers" % (args.log_n, args.log_n),
+                   "log_n": args.log_n, "seed": 20260924, "cpu_sample_log_n": args.cpu_log_n},
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -163,7 +164,7 @@ def b200_arm(args):
     n = 1 << log_n
     t0 = time.time()
     setup = pb.Setup.generate(TAU, n, ctx=ctx)
-    circ = syn.build_circuit(log_n, seed=20260924 + rank, n_public=2)
+    circ = syn.build_circuit(log_n, seed=20260924, n_public=2)
     pk, A, B, C, public = syn.circuit_arrays(circ)
     prover = pb.Prover.from_arrays(setup, n, pk)
     setup_s = time.time() - t0
@@ -249,10 +250,19 @@ def b200_arm(args):
         ms = timed_local(torch, stream, commit, 5)
         comp["g1_msm_fixed_base_2^%d" % log_n] = {"ms": ms / 5, "points_per_s": n / (ms / 5 * 1e-3)}
 
+    shard_ms = None
+    if world > 1:
+        # one proof across all GPUs: point-sharded commitments, one NCCL allgather per round (parallel.py)
+        from plonkathon_b200 import parallel
+        sp = parallel.ShardedProver.from_arrays(setup, n, pk)  # every rank holds the same circuit instance
+        assert sp.prove_arrays(A, B, C, public) == ref_proof, "sharded proof differs from the single-GPU proof"
+        shard_ms = timed(lambda: sp.prove_arrays(A, B, C, public), args.steps) / args.steps
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if shard_ms is not None:
+        comp["one_proof_across_%d_gpus_sharded_msm" % world] = {"ms": shard_ms, "proofs_per_s": 1e3 / shard_ms}
     hbm_gbs, peak_src = measured_peaks()
     proofs = args.steps * world
     value = proofs / (ms_dev * 1e-3)
@@ -260,7 +270,12 @@ def b200_arm(args):
     # dominant kernel: MSM bucket accumulation.  Algorithmic bytes: 96 B per point (64 B affine point + 32 B
     # scalar) x n points per launch (one launch per commitment).
     acc_avg_ms = acc_ms / max(1, acc_cnt)
-    achieved = 96.0 * n / (acc_avg_ms * 1e-3) / 1e9
+    # 9 commitments x n points per proof go through the accumulation kernel (4 batched launches per proof)
+    points_per_launch = 9.0 * n * args.steps / max(1, acc_cnt)
+    achieved = 96.0 * points_per_launch / (acc_avg_ms * 1e-3) / 1e9
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/r01_ncu_msm_acc.md:
+    # 5.56 GB for a 3-commitment launch at 2^20), scaled to this run's average launch
+    traffic = 5.557e9 * (points_per_launch / (3.0 * (1 << 20))) if log_n == 20 else None
     ntt_avg_ms = ntt_ms / max(1, ntt_cnt)
     line = {
         "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
@@ -275,10 +290,14 @@ def b200_arm(args):
                 "d2h_bytes_per_step": 768, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_msm_seg_accumulate", "achieved": achieved, "peak": hbm_gbs,
-                     "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": 96.0 * points_per_launch,
+                     "modmul_ceiling_frac": (10.0 * 13 * points_per_launch / (acc_avg_ms * 1e-3)) / 65.4e9,
                      "launches": int(acc_cnt), "avg_launch_ms": acc_avg_ms,
                      "share_of_step": acc_ms / ms_dev if ms_dev else None,
-                     "note": "integer-pipe bound (IMAD), not HBM bound: see DESIGN.md"},
+                     "note": "integer-pipe bound (ncu: fmaheavy pipe 87% active), not HBM bound; modmul_ceiling_frac = Montgomery "
+                             "products/s of this kernel / 65.4e9 measured peak; traffic is 18x the algorithmic bytes because "
+                             "every point is gathered once per window (13) from the fixed-base table: see DESIGN.md"},
         "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "launches": int(ntt_cnt), "avg_launch_ms": ntt_avg_ms,
                          "share_of_step": ntt_ms / ms_dev if ms_dev else None},
         "components": comp,

@@ -338,3 +338,71 @@ def test_prove_2p20_gates_verifies(pb):
     bad = dict(proof)
     bad["z_shifted_eval"] = (bad["z_shifted_eval"] + 1) % R
     assert not O.verify_proof_trapdoor(n, vk, bad, public, TAU)
+
+
+def test_prove_many_public_inputs_dense_path(pb):
+    """more than 8 public inputs take the generic (interpolated PI) path; same bytes as the oracle"""
+    from plonkathon_b200 import synthetic as syn
+    log_n = 6
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=3, n_public=11)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    raw = pb.Prover.from_arrays(setup, n, pk).prove_arrays(A, B, C, public)
+    S1, S2, S3 = syn.permutation_polys(c.wire_L, c.wire_R, c.wire_O, n, c.n_constraints)
+    opk = O.Preprocessed(n, c.QM, c.QL, c.QR, c.QO, c.QC, S1, S2, S3)
+    osetup = O.Setup([(p[0].n, p[1].n) for p in setup.powers_of_x], None)
+    a, b, cc = c.wires_values()
+    assert raw == O.proof_bytes(O.Prover(osetup, opk).prove(a, b, cc, c.public_values()))
+
+
+def test_verification_key_object(pb, setup):
+    """Setup.verification_key(pk) (setup.py:75-77) with a CommonPreprocessedInput-shaped object"""
+    from collections import namedtuple
+    entry, arr = load_circuit("one_public")
+    P = namedtuple("Poly", "values basis")
+    PK = namedtuple("PK", "group_order QM QL QR QO QC S1 S2 S3")
+    pk = PK(8, *[pb.Polynomial(S(pb, arr[k]), pb.Basis.LAGRANGE) for k in ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3")])
+    vk = setup.verification_key(pk)
+    for key in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+        got, exp = getattr(vk, key), pt(entry["vk"][key])
+        assert (got is None and exp is None) or (got[0].n, got[1].n) == exp, key
+    assert vk.w == int(entry["vk"]["w"]) and vk.group_order == 8
+    assert (tuple(vk.X_2[0]), tuple(vk.X_2[1])) == tuple(tuple(int(c) for c in row) for row in entry["vk"]["X_2"])
+
+
+def test_msm_skewed_scalars_2p18(pb):
+    """witness-like scalar distribution (half zeros, a quarter ones, small constants, the rest uniform) through
+    the fixed-base commit path: exact answer by folding per base point, and no load-imbalance blow-up"""
+    import time
+    from plonkathon_b200 import _lib
+    n = 1 << 18
+    setup = pb.Setup.generate(TAU, n)
+    rng = np.random.default_rng(5)
+    sc = _random_fr(n, 17)
+    kind = rng.integers(0, 8, size=n)
+    sc[kind < 4] = 0
+    ones = (kind == 4) | (kind == 5)
+    sc[ones] = 0
+    sc[ones, 0] = 1
+    small = kind == 6
+    sc[small] = 0
+    sc[small, 0] = rng.integers(2, 1000, size=int(small.sum()))
+    out = ctypes.create_string_buffer(64)
+    ident = ctypes.c_int(0)
+    dev = __import__("torch").from_numpy(sc.view(np.int32)).cuda()
+    t0 = time.time()
+    _lib.check(_lib.lib().pb200_srs_commit_coeffs(setup.ctx.handle, setup._srs, ctypes.c_void_p(dev.data_ptr()), n, 0,
+                                                  out, ctypes.byref(ident)))
+    dt = time.time() - t0
+    # expected: sum_i s_i tau^i * G
+    acc, cur = 0, 1
+    sc_int = [int.from_bytes(sc[i].tobytes(), "little") for i in range(n)]
+    for s_i in sc_int:
+        if s_i:
+            acc += s_i * cur
+        cur = cur * TAU % R
+    exp = O.g1_multiply(O.G1, acc % R)
+    got = (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little"))
+    assert got == exp
+    assert dt < 0.5, "skewed MSM took %.3f s" % dt
