@@ -219,6 +219,14 @@ class Prover:
         """commitments a round produced (overridden by the multi-GPU prover, which gathers partial sums)"""
         return _pts(raw, count)
 
+    def fft_expand(self, x):
+        """prover.py:308-309 -- x.to_coset_extended_lagrange(self.fft_cofactor)."""
+        return x.to_coset_extended_lagrange(self.fft_cofactor, ctx=self.ctx)
+
+    def expanded_evals_to_coeffs(self, x):
+        """prover.py:311-312 -- x.coset_extended_lagrange_to_coeffs(self.fft_cofactor)."""
+        return x.coset_extended_lagrange_to_coeffs(self.fft_cofactor, ctx=self.ctx)
+
     def rlc(self, term_1, term_2):
         """prover.py:314-315."""
         return term_1 + term_2 * self.beta + self.gamma
