@@ -56,6 +56,15 @@ int pb200_fr_from_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n
 int pb200_fr_ntt(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse);
 int pb200_fr_ntt_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n, int inverse);
 
+/* Multi-GPU slab NTT (poly.py:113-149 across G = 2^log_g GPUs, N = G * 2^log_m):
+ *  1. every rank h transforms the decimated sequence x[h::G] locally   -> pb200_fr_ntt_decimated(stride G, offset h)
+ *  2. ONE allgather of the G sub-spectra (the caller's NCCL collective) -> d_sub = [G][2^log_m]
+ *  3. every rank computes its contiguous output slab X[slab*M .. (slab+1)*M) -> pb200_fr_ntt_slab_combine */
+int pb200_fr_ntt_decimated(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_m, int inverse, uint64_t stride,
+                           uint64_t offset);
+int pb200_fr_ntt_slab_combine(pb200_ctx* ctx, const void* d_sub, void* d_out, unsigned log_m, unsigned log_g,
+                              uint64_t slab, int inverse);
+
 /* poly.py:156-163  to_coset_extended_lagrange(offset): n Lagrange values -> 4n evaluations on
  * offset * <w_4n>.  h_offset: 32-byte canonical Fr. */
 int pb200_fr_coset_extend(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset);

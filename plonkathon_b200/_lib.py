@@ -40,6 +40,8 @@ def _load():
         "pb200_fr_from_mont": (I, [V, V, V, U64]),
         "pb200_fr_ntt": (I, [V, V, V, U, I]),
         "pb200_fr_ntt_host": (I, [V, V, V, U, I]),
+        "pb200_fr_ntt_decimated": (I, [V, V, V, U, I, U64, U64]),
+        "pb200_fr_ntt_slab_combine": (I, [V, V, V, U, U, U64, I]),
         "pb200_fr_coset_extend": (I, [V, V, V, U, V]),
         "pb200_fr_coset_extend_host": (I, [V, V, V, U, V]),
         "pb200_fr_coset_to_coeffs": (I, [V, V, V, U, V]),

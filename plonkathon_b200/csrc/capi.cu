@@ -13,6 +13,9 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
              const Fr* out_scale);
 void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
 Fr fr_from_u64(uint64_t x);
+void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
+                     const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
+void ntt_slab_combine(Context* ctx, const Fr* sub, Fr* out, int log_m, int log_g, uint64_t slab, bool inverse);
 // poly_ops.cu
 void fr_to_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
 void fr_from_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
@@ -162,6 +165,22 @@ int pb200_fr_from_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n
 int pb200_fr_ntt(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse) {
   PB_API_BEGIN
   ntt_run(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, inverse != 0, (uint64_t)1 << log_n, nullptr, nullptr);
+  PB_API_END
+}
+
+int pb200_fr_ntt_decimated(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_m, int inverse, uint64_t stride,
+                           uint64_t offset) {
+  PB_API_BEGIN
+  PB_CHECK(stride >= 1, "bad stride");
+  ntt_run_strided(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_m, inverse != 0, (uint64_t)1 << log_m, nullptr, nullptr,
+                  stride, offset);
+  PB_API_END
+}
+int pb200_fr_ntt_slab_combine(pb200_ctx* ctx, const void* d_sub, void* d_out, unsigned log_m, unsigned log_g,
+                              uint64_t slab, int inverse) {
+  PB_API_BEGIN
+  PB_CHECK(log_g >= 1 && log_g <= 3 && slab < ((uint64_t)1 << log_g), "slab NTT supports 2, 4 or 8 ranks");
+  ntt_slab_combine(C(ctx), (const Fr*)d_sub, (Fr*)d_out, (int)log_m, (int)log_g, slab, inverse != 0);
   PB_API_END
 }
 

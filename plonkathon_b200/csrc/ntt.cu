@@ -98,6 +98,7 @@ struct PassParams {
   const Fr* in_scale;   // optional multiply-on-load table, indexed by global input index
   const Fr* out_scale;  // optional multiply-on-store table, indexed by global output index
   uint64_t n_in;        // input indices >= n_in read as zero
+  uint64_t in_mul, in_add;  // physical input index = logical * in_mul + in_add (strided sub-sequence, first pass)
   uint32_t log_b, log_cc, t_lo_count, b_fastest_load, has_final_scale;
   uint64_t r_hi, r_lo, r_cs, r_bs;
   uint64_t w_hi, w_lo, w_cs, w_bs;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256, 2) k_ntt_pass(PassParams p) {
     uint64_t gi = rbase + (uint64_t)c * p.r_cs + (uint64_t)b * p.r_bs;
     Fr x = Fr::zero();
     if (gi < p.n_in) {
-      x = ld_global(p.in + gi);
+      x = ld_global(p.in + gi * p.in_mul + p.in_add);
       if (p.in_scale) x = fp_mul(x, ld_global(p.in_scale + gi));
     }
     uint32_t br = p.log_b ? (__brev(b) >> (32 - p.log_b)) : 0;
@@ -441,8 +442,16 @@ Context::~Context() {
 // in_scale / out_scale: optional per-index multiplier tables.  `out` may alias `in` when
 // n_in == 2^log_n.  Data form is irrelevant (the transform is linear and the twiddles are in
 // Montgomery form): Montgomery in -> Montgomery out, canonical in -> canonical out.
+void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
+                     const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
+
 void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
              const Fr* in_scale, const Fr* out_scale) {
+  ntt_run_strided(ctx, in, out, log_n, inverse, n_in, in_scale, out_scale, 1, 0);
+}
+
+void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
+                     const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add) {
   NttPlan* plan = get_plan(ctx, log_n, inverse);
   const uint64_t N = (uint64_t)1 << log_n;
   int np = (int)plan->passes.size();
@@ -457,6 +466,8 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
     q.in = (i == 0) ? in : tmp;
     q.out = (i == np - 1) ? out : tmp;
     q.n_in = (i == 0) ? n_in : N;
+    q.in_mul = (i == 0) ? in_mul : 1;
+    q.in_add = (i == 0) ? in_add : 0;
     q.in_scale = (i == 0) ? in_scale : nullptr;
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
@@ -465,6 +476,38 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
     ctx->time_end(1);
     ctx->launches++;
   }
+  PB_CUDA(cudaGetLastError());
+}
+
+// ---- multi-GPU slab NTT: the join after the allgather ------------------------------------------------
+// N = G * M.  Rank h transformed the decimated sequence x[h::G] into Y_h (size M).  With all G sub-spectra
+// gathered (sub = [G][M]), the contiguous output slab s is X[s*M + t] = sum_h w_N^(h (s M + t)) Y_h[t]: a
+// length-G DFT per element, evaluated by Horner in w_N^k (G - 1 products; G <= 8 in one box).
+__global__ void __launch_bounds__(128) k_ntt_slab_combine(const Fr* sub, Fr* out, uint64_t M, uint32_t G, uint64_t slab,
+                                                          Fr wN, Fr scale) {
+  const int CH = 16;
+  uint64_t t0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * CH;
+  if (t0 >= M) return;
+  Fr w = fp_pow_u64(wN, slab * M + t0);
+  for (int j = 0; j < CH && t0 + j < M; j++) {
+    uint64_t t = t0 + j;
+    Fr acc = ld_global(sub + (uint64_t)(G - 1) * M + t);
+    for (int h = (int)G - 2; h >= 0; h--) acc = fp_add(fp_mul(acc, w), ld_global(sub + (uint64_t)h * M + t));
+    st_global(out + t, fp_mul(acc, scale));
+    w = fp_mul(w, wN);
+  }
+}
+
+// inverse: the sub-transforms already carry 1/M, the join adds 1/G
+void ntt_slab_combine(Context* ctx, const Fr* sub, Fr* out, int log_m, int log_g, uint64_t slab, bool inverse) {
+  uint64_t M = (uint64_t)1 << log_m;
+  uint32_t G = 1u << log_g;
+  Fr wN = fr_root_of_unity(log_m + log_g);
+  Fr scale = Fr::one();
+  if (inverse) { wN = fp_inv(wN); scale = fp_inv(fr_from_u64(G)); }
+  uint64_t threads = (M + 15) / 16;
+  k_ntt_slab_combine<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(sub, out, M, G, slab, wN, scale);
+  ctx->launches++;
   PB_CUDA(cudaGetLastError());
 }
 

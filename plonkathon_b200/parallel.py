@@ -117,3 +117,40 @@ class ShardedProver(Prover):
         proof = ctypes.create_string_buffer(768)
         _lib.check(L.pb200_prover_serialize(self._h, proof))
         return proof.raw
+
+
+# ------------------------------------------------------------------------------------------------
+# slab-sharded NTT (north_star: "NTT by coefficient-slab across the GPUs with a single allgather at the join")
+# ------------------------------------------------------------------------------------------------
+def slab_ntt_plan(log_n: int, world: int):
+    """N = 2^log_n over `world` = 2^log_g ranks -> (log_m, log_g): rank h owns the decimated input x[h::world]
+    and produces the contiguous output slab [h*M, (h+1)*M), M = N / world."""
+    log_g = world.bit_length() - 1
+    assert world == 1 << log_g and 1 <= log_g <= 3 and log_n > log_g, "slab NTT: 2, 4 or 8 ranks"
+    return log_n - log_g, log_g
+
+
+def slab_ntt(x_full, log_n: int, inverse: bool = False, group=None, ctx: Optional[_lib.Context] = None):
+    """Distributed NTT of the length-2^log_n vector `x_full` (a CUDA uint8/int32 tensor of N*32 bytes holding
+    canonical or Montgomery Fr elements, present on every rank; only the rank's decimated part is read).
+    Returns this rank's contiguous output slab as a CUDA tensor [M, 32] uint8.  One NCCL allgather."""
+    import torch
+    import torch.distributed as dist
+    ctx = ctx or _lib.default_context()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    log_m, log_g = slab_ntt_plan(log_n, world)
+    M = 1 << log_m
+    L = _lib.lib()
+    vp = ctypes.c_void_p
+    local = torch.empty((M, 32), dtype=torch.uint8, device=x_full.device)
+    _lib.check(L.pb200_fr_ntt_decimated(ctx.handle, vp(x_full.data_ptr()), vp(local.data_ptr()), log_m,
+                                        1 if inverse else 0, world, rank))
+    ctx.sync()  # the library stream is not torch's: make the sub-spectrum visible to the collective
+    sub = torch.empty((world, M, 32), dtype=torch.uint8, device=x_full.device)
+    dist.all_gather_into_tensor(sub, local, group=group)  # the one exchange step
+    torch.cuda.current_stream().synchronize()
+    out = torch.empty((M, 32), dtype=torch.uint8, device=x_full.device)
+    _lib.check(L.pb200_fr_ntt_slab_combine(ctx.handle, vp(sub.data_ptr()), vp(out.data_ptr()), log_m, log_g, rank,
+                                           1 if inverse else 0))
+    ctx.sync()
+    return out

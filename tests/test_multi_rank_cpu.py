@@ -78,3 +78,42 @@ def test_shard_range_partitions():
                 assert f == pos
                 pos += c
             assert pos == n
+
+
+def _ntt_cpu_worker(rank, world, port, log_n, q):
+    """the slab-NTT decomposition of parallel.slab_ntt with the oracle standing in for the CUDA kernels"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from plonkathon_b200 import parallel
+    n = 1 << log_n
+    rng = random.Random(3)
+    x = [rng.randrange(O.R_MOD) for _ in range(n)]
+    log_m, log_g = parallel.slab_ntt_plan(log_n, world)
+    M = 1 << log_m
+    local = O.fft(x[rank::world])                      # step 1: local transform of the decimated sequence
+    buf = b"".join(v.to_bytes(32, "little") for v in local)
+    gathered = parallel.allgather_bytes(buf)           # step 2: the one allgather
+    Y = [[int.from_bytes(g[32 * t:32 * t + 32], "little") for t in range(M)] for g in gathered]
+    w = O.root_of_unity(n)
+    slab = []
+    for t in range(M):                                 # step 3: length-G DFT per element of the slab
+        k = rank * M + t
+        slab.append(sum(pow(w, h * k, O.R_MOD) * Y[h][t] for h in range(world)) % O.R_MOD)
+    q.put((rank, slab == O.fft(x)[rank * M:(rank + 1) * M]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_ntt_decomposition_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ntt_cpu_worker, args=(r, 2, port, 8, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
