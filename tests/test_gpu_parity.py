@@ -406,3 +406,44 @@ def test_msm_skewed_scalars_2p18(pb):
     got = (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little"))
     assert got == exp
     assert dt < 0.5, "skewed MSM took %.3f s" % dt
+
+
+def test_error_behaviour_matches_reference(pb, setup):
+    """errors surface as the reference's exception types at the boundary"""
+    big = pb.Polynomial(S(pb, list(range(4096))), pb.Basis.LAGRANGE)
+    with pytest.raises(Exception, match="Not enough powers"):  # SRS holds 2^11 powers (setup.py:27)
+        setup.commit(big)
+    with pytest.raises(AssertionError):  # setup.py:67 asserts the LAGRANGE basis
+        setup.commit(pb.Polynomial(S(pb, [1, 2]), pb.Basis.MONOMIAL))
+    with pytest.raises(AssertionError):  # poly.py:15 isinstance check
+        pb.Polynomial([1, 2], pb.Basis.LAGRANGE)
+    with pytest.raises(AssertionError):  # power-of-two length
+        pb.Polynomial(S(pb, [1, 2, 3]), pb.Basis.MONOMIAL).fft()
+    with pytest.raises(AssertionError):  # poly.py:157 basis assert
+        pb.Polynomial(S(pb, [1, 2]), pb.Basis.MONOMIAL).to_coset_extended_lagrange(pb.Scalar(3))
+    # scalars >= r and negative ints are reduced like curve.py:41
+    g = (pb.FQ(1), pb.FQ(2))
+    a = pb.ec_lincomb([(g, -1), (g, R + 3)])
+    assert (a[0].n, a[1].n) == O.g1_multiply(O.G1, 2)
+    assert pb.ec_mul(g, pb.Scalar(5)) == O.g1_multiply(O.G1, 5)
+    assert pb.ec_mul(None, 5) is None and pb.ec_lincomb([(g, 0)]) is None
+
+
+def test_prove_2p22_gates_runs(pb):
+    """BASELINE.json's largest configuration size (2^22 gates, 4n = 2^24 domain) on one GPU: the proof is
+    deterministic and its commitments are on the curve (full verification is covered at 2^20)."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60 * 2 ** 30:
+        pytest.skip("needs ~40 GB of HBM")
+    from plonkathon_b200 import synthetic as syn
+    log_n = 22
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=9, n_public=2)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    prover = pb.Prover.from_arrays(setup, n, pk)
+    raw = prover.prove_arrays(A, B, C, public)
+    assert prover.prove_arrays(A, B, C, public) == raw
+    proof = O.proof_from_bytes(raw)
+    for k in ("a_1", "b_1", "c_1", "z_1", "t_lo_1", "t_mid_1", "t_hi_1", "W_z_1", "W_zw_1"):
+        assert O.g1_is_on_curve(proof[k])
