@@ -4,10 +4,12 @@
 // setup.py:66-72 (`Setup.commit`).  The result sum_i s_i * P_i is algorithm-independent, so the
 // reference's bit-sliced power-set method is replaced by:
 //   1. signed-digit window slicing of every scalar (c-bit windows, digits in [-2^(c-1), 2^(c-1)]),
-//      with a global histogram of bucket loads                                  (k_msm_digits)
+//      with a global histogram of bucket loads                                  (k_msm_histogram)
 //   2. exclusive scan of the histogram                                           (k_scan_*)
 //   3. counting-sort scatter of (point index, sign) by bucket                    (k_msm_scatter)
-//   4. bucket accumulation: XYZZ accumulator += affine point (8M+2S, no inversion) (k_msm_accumulate)
+//   4. load-balanced bucket accumulation over fixed segments of the sorted entries: XYZZ accumulator +=
+//      affine point (8M+2S, no inversion), SIMT-uniform loop                     (k_msm_seg_accumulate)
+//      + stitching of buckets that cross a segment boundary                      (k_msm_stitch[_heavy])
 //   5. bucket reduction sum_b (b+1) * B_b by running sums over bucket groups     (k_bucket_groups)
 //      followed by a tree sum of the group results                               (k_sum_points)
 //   6. the few remaining group operations (window Horner, one inversion to affine) on the host,
@@ -492,7 +494,6 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     k_scan_tile_sums<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums);
     k_scan_tiles<<<1, 256, 0, st>>>(tile_sums, n_tiles, offsets.as<uint32_t>() + g.nb);
     k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums, offsets.as<uint32_t>());
-    ctx->launches += 2;
   }
   k_msm_scatter<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
                                                      counts.as<uint32_t>(), sorted.as<uint32_t>());
@@ -516,7 +517,6 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     k_msm_stitch<<<(n_seg + 127) / 128, 128, 0, st>>>(offsets.as<uint32_t>(), g.nb, L, n_seg, slots, slot_bucket,
                                                      own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, 16);
     k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, buckets.as<G1XYZZ>());
-    ctx->launches += 2;
   }
   k_bucket_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(buckets.as<G1XYZZ>(), g.half, gsz, n_groups,
                                                          groups.as<G1XYZZ>());
@@ -527,12 +527,12 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     if (mid > 1) {
       k_sum_points<<<dim3(mid, n_windows_out), 128, 0, st>>>(groups.as<G1XYZZ>(), per, level1);
       k_sum_points<<<dim3(1, n_windows_out), 128, 0, st>>>(level1, mid, wsums.as<G1XYZZ>());
-      ctx->launches++;
+      ctx->launches++;  // the second tree level
     } else {
       k_sum_points<<<dim3(1, n_windows_out), 128, 0, st>>>(groups.as<G1XYZZ>(), per, wsums.as<G1XYZZ>());
     }
   }
-  ctx->launches += 6;
+  ctx->launches += 10;  // histogram, 3 x scan, scatter, accumulate, stitch, stitch_heavy, bucket_groups, sum_points
   PB_CUDA(cudaGetLastError());
   std::vector<G1XYZZ> ws(n_windows_out);
   PB_CUDA(cudaMemcpyAsync(ws.data(), wsums.p, n_windows_out * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));

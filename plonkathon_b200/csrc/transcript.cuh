@@ -167,11 +167,6 @@ class Transcript {
   }
 
  private:
-  static Fr small(uint32_t v) {
-    Fr a = Fr::zero();
-    a.v[0] = v;
-    return a;
-  }
   Strobe128 strobe_;
 };
 

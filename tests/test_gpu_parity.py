@@ -447,3 +447,40 @@ def test_prove_2p22_gates_runs(pb):
     proof = O.proof_from_bytes(raw)
     for k in ("a_1", "b_1", "c_1", "z_1", "t_lo_1", "t_mid_1", "t_hi_1", "W_z_1", "W_zw_1"):
         assert O.g1_is_on_curve(proof[k])
+
+
+# ------------------------------------------------------------------ exact full-size parity vs the C oracle
+@pytest.mark.parametrize("logn", [20])
+def test_ntt_2p20_exact_vs_c_oracle(pb, logn):
+    """BASELINE.json configs[1]: Fr NTT forward + inverse at 2^20, every element compared with the C
+    restatement of poly.py:113-149 (oracle/c/plonk_oracle.c, itself checked against the pinned Python oracle)"""
+    from oracle import c_oracle as C
+    n = 1 << logn
+    x = _random_fr(n, 42)
+    xb = x.view(np.uint8).reshape(n, 32)
+    assert np.array_equal(_raw_ntt(pb, x, logn, 0).view(np.uint8).reshape(n, 32), C.fft(xb, False))
+    assert np.array_equal(_raw_ntt(pb, x, logn, 1).view(np.uint8).reshape(n, 32), C.fft(xb, True))
+
+
+def test_msm_2p18_distinct_points_exact_vs_c_oracle(pb):
+    """BASELINE.json configs[2] family: KZG-style MSM over 2^18 DISTINCT points (structured SRS exported from
+    the device) with uniform scalars, both MSM modes, against the C restatement of curve.py:38-44"""
+    from oracle import c_oracle as C
+    from plonkathon_b200 import _lib
+    n = 1 << 18
+    setup = pb.Setup.generate(TAU, n)
+    buf = ctypes.create_string_buffer(64 * n)
+    _lib.check(_lib.lib().pb200_srs_export(setup.ctx.handle, setup._srs, buf, 0, n))
+    pts = np.frombuffer(buf.raw, dtype=np.uint8).reshape(n, 64)
+    sc = _random_fr(n, 77)
+    exp = C.g1_lincomb(pts, sc.view(np.uint8).reshape(n, 32))
+    out = ctypes.create_string_buffer(64)
+    ident = ctypes.c_int(0)
+    _lib.check(_lib.lib().pb200_g1_msm_host(setup.ctx.handle, pts.ctypes.data_as(ctypes.c_void_p),
+                                            sc.ctypes.data_as(ctypes.c_void_p), n, out, ctypes.byref(ident)))
+    assert (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little")) == exp
+    import torch
+    dev = torch.from_numpy(sc.view(np.int32)).cuda()
+    _lib.check(_lib.lib().pb200_srs_commit_coeffs(setup.ctx.handle, setup._srs, ctypes.c_void_p(dev.data_ptr()), n, 0,
+                                                  out, ctypes.byref(ident)))
+    assert (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little")) == exp
