@@ -38,11 +38,42 @@ def bytes_to_scalars(raw: bytes):
 
 
 class Polynomial:
-    def __init__(self, values, basis: Basis):
-        assert all(isinstance(x, Scalar) for x in values)
+    """``values`` is the reference's list[Scalar].  Results of the GPU transforms stay resident in HBM (a
+    canonical [n, 32]-byte tensor) and only materialise ``values`` when somebody reads them, so chains such as
+    ``p.ifft().fft()``, ``setup.commit(p.fft())`` or ``p.to_coset_extended_lagrange(k)
+    .coset_extended_lagrange_to_coeffs(k)`` cross the Python-object boundary once."""
+
+    def __init__(self, values, basis: Basis, _dev=None):
         assert isinstance(basis, Basis)
-        self.values = values
+        if _dev is None:
+            assert all(isinstance(x, Scalar) for x in values)
+        self._values = values
+        self._dev = _dev
         self.basis = basis
+
+    @property
+    def values(self):
+        if self._values is None:
+            self._values = bytes_to_scalars(self._dev.cpu().numpy().tobytes())
+        return self._values
+
+    @values.setter
+    def values(self, v):
+        self._values = v
+        self._dev = None
+
+    def __len__(self):
+        return len(self._values) if self._values is not None else int(self._dev.shape[0])
+
+    def _device(self, ctx):
+        """canonical [n, 32] uint8 CUDA tensor holding the values (uploaded once)"""
+        import torch
+        if self._dev is None:
+            raw = bytearray(scalars_to_bytes(self._values))
+            t = torch.frombuffer(raw, dtype=torch.uint8).reshape(-1, 32) if raw else torch.empty((0, 32), dtype=torch.uint8)
+            self._dev = t.to(torch.device("cuda", ctx.device))
+            torch.cuda.current_stream(self._dev.device).synchronize()  # the library runs on its own stream
+        return self._dev
 
     def __eq__(self, other):
         return (self.basis == other.basis) and (self.values == other.values)
@@ -92,18 +123,27 @@ class Polynomial:
     def _ctx(self, ctx):
         return ctx or _lib.default_context()
 
+    def _run(self, ctx, out_rows, call):
+        import torch
+        ctx = self._ctx(ctx)
+        d_in = self._device(ctx)
+        d_out = torch.empty((out_rows, 32), dtype=torch.uint8, device=d_in.device)
+        torch.cuda.current_stream(d_in.device).synchronize()
+        call(ctx, ctypes.c_void_p(d_in.data_ptr()), ctypes.c_void_p(d_out.data_ptr()))
+        ctx.sync()
+        return d_out
+
     def fft(self, inv=False, ctx: Optional[_lib.Context] = None):
         """poly.py:113-145."""
         if inv:
             assert self.basis == Basis.LAGRANGE
         else:
             assert self.basis == Basis.MONOMIAL
-        n = len(self.values)
+        n = len(self)
         log_n = _log2_exact(n)
-        raw = scalars_to_bytes(self.values)
-        out = ctypes.create_string_buffer(len(raw))
-        _lib.check(_lib.lib().pb200_fr_ntt_host(self._ctx(ctx).handle, raw, out, log_n, 1 if inv else 0))
-        return Polynomial(bytes_to_scalars(out.raw), Basis.MONOMIAL if inv else Basis.LAGRANGE)
+        out = self._run(ctx, n, lambda c, i, o: _lib.check(
+            _lib.lib().pb200_fr_ntt(c.handle, i, o, log_n, 1 if inv else 0)))
+        return Polynomial(None, Basis.MONOMIAL if inv else Basis.LAGRANGE, _dev=out)
 
     def ifft(self, ctx=None):
         """poly.py:147-148."""
@@ -112,29 +152,32 @@ class Polynomial:
     def to_coset_extended_lagrange(self, offset, ctx=None):
         """poly.py:156-163."""
         assert self.basis == Basis.LAGRANGE
-        n = len(self.values)
-        raw = scalars_to_bytes(self.values)
-        out = ctypes.create_string_buffer(4 * len(raw))
+        n = len(self)
+        log_n = _log2_exact(n)
         off = (int(offset) % CURVE_ORDER).to_bytes(32, "little")
-        _lib.check(_lib.lib().pb200_fr_coset_extend_host(self._ctx(ctx).handle, raw, out, _log2_exact(n), off))
-        return Polynomial(bytes_to_scalars(out.raw), Basis.LAGRANGE)
+        out = self._run(ctx, 4 * n, lambda c, i, o: _lib.check(
+            _lib.lib().pb200_fr_coset_extend(c.handle, i, o, log_n, off)))
+        return Polynomial(None, Basis.LAGRANGE, _dev=out)
 
     def coset_extended_lagrange_to_coeffs(self, offset, ctx=None):
         """poly.py:169-177."""
         assert self.basis == Basis.LAGRANGE
-        n = len(self.values)
-        raw = scalars_to_bytes(self.values)
-        out = ctypes.create_string_buffer(len(raw))
+        n = len(self)
+        log_n = _log2_exact(n)
         off = (int(offset) % CURVE_ORDER).to_bytes(32, "little")
-        _lib.check(_lib.lib().pb200_fr_coset_to_coeffs_host(self._ctx(ctx).handle, raw, out, _log2_exact(n), off))
-        return Polynomial(bytes_to_scalars(out.raw), Basis.MONOMIAL)
+        out = self._run(ctx, n, lambda c, i, o: _lib.check(
+            _lib.lib().pb200_fr_coset_to_coeffs(c.handle, i, o, log_n, off)))
+        return Polynomial(None, Basis.MONOMIAL, _dev=out)
 
     def barycentric_eval(self, x, ctx=None):
         """poly.py:181-195."""
         assert self.basis == Basis.LAGRANGE
-        n = len(self.values)
-        raw = scalars_to_bytes(self.values)
+        import torch
+        ctx = self._ctx(ctx)
+        d_in = self._device(ctx)
+        torch.cuda.current_stream(d_in.device).synchronize()
         out = ctypes.create_string_buffer(32)
         xb = (int(x) % CURVE_ORDER).to_bytes(32, "little")
-        _lib.check(_lib.lib().pb200_fr_barycentric_eval_host(self._ctx(ctx).handle, raw, _log2_exact(n), xb, out))
+        _lib.check(_lib.lib().pb200_fr_barycentric_eval(ctx.handle, ctypes.c_void_p(d_in.data_ptr()),
+                                                        _log2_exact(len(self)), xb, out))
         return Scalar(int.from_bytes(out.raw, "little"))

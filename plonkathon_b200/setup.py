@@ -108,14 +108,16 @@ class Setup:
     def commit(self, values: Polynomial):
         """setup.py:66-72."""
         assert values.basis == Basis.LAGRANGE
-        n = len(values.values)
+        n = len(values)
         if n > self._n:
             raise Exception("Not enough powers in setup")
-        raw = scalars_to_bytes(values.values)
+        import torch
+        d_vals = values._device(self.ctx)  # stays in HBM if it came out of a transform
+        torch.cuda.current_stream(d_vals.device).synchronize()
         out = ctypes.create_string_buffer(64)
         ident = ctypes.c_int(0)
-        _lib.check(_lib.lib().pb200_srs_commit_lagrange_host(
-            self.ctx.handle, self._srs, raw, _log2_exact(n), out, ctypes.byref(ident)))
+        _lib.check(_lib.lib().pb200_srs_commit_lagrange(
+            self.ctx.handle, self._srs, ctypes.c_void_p(d_vals.data_ptr()), _log2_exact(n), out, ctypes.byref(ident)))
         return _pt_from(out.raw, ident.value)
 
     def verification_key(self, pk) -> VerificationKey:

@@ -484,3 +484,22 @@ def test_msm_2p18_distinct_points_exact_vs_c_oracle(pb):
     _lib.check(_lib.lib().pb200_srs_commit_coeffs(setup.ctx.handle, setup._srs, ctypes.c_void_p(dev.data_ptr()), n, 0,
                                                   out, ctypes.byref(ident)))
     assert (int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little")) == exp
+
+
+def test_polynomial_results_stay_device_resident(pb, setup):
+    """transform results keep their data in HBM and materialise list[Scalar] lazily; chains and commit agree
+    with the oracle"""
+    rng = random.Random(8)
+    v = [rng.randrange(R) for _ in range(256)]
+    p = pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE)
+    c = p.ifft()
+    assert c._values is None and len(c) == 256  # nothing crossed back yet
+    back = c.fft()
+    assert back == p and vals(c) == O.ifft(v)
+    off = pb.Scalar(rng.randrange(1, R))
+    ext = p.to_coset_extended_lagrange(off)
+    assert len(ext) == 1024 and vals(ext.coset_extended_lagrange_to_coeffs(off))[:256] == O.ifft(v)
+    got = setup.commit(c.fft())  # device-resident input
+    assert (got[0].n, got[1].n) == O.Setup.from_file(PTAU_HEAD).commit(v)
+    c.values = S(pb, [1, 2, 3, 4])  # assigning values drops the device copy
+    assert len(c) == 4 and vals(c.fft()) == O.fft([1, 2, 3, 4])
