@@ -3,6 +3,7 @@
 // tests/test_host_arith.py through ctypes; never linked into libplonk_b200.so.
 #include "field.cuh"
 #include "curve.cuh"
+#include "fieldd.cuh"
 #include <cstring>
 using namespace pb200;
 
@@ -30,6 +31,13 @@ int hs_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_
     st(out, r);                                                  \
   }
   if (field == 0) RUN(Fr) else RUN(Fq)
+  return 0;
+}
+
+// FP64-pipe multiplier: out = a * b * 2^-260 mod p on plain integers a, b < p (8 x u32 limbs in and out)
+int hs_fieldd_mul(int field, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  if (field == 0) { Fr r = fpd_to_u32(fpd_mul(fpd_from_u32(ld<Fr>(a)), fpd_from_u32(ld<Fr>(b)))); st(out, r); }
+  else { Fq r = fpd_to_u32(fpd_mul(fpd_from_u32(ld<Fq>(a)), fpd_from_u32(ld<Fq>(b)))); st(out, r); }
   return 0;
 }
 
