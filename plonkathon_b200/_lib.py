@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplonk_b200.so")
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_HERE, "libplonk_b200.so")  # PB200_LIB: tuning experiments
 
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 

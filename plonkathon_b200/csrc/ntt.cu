@@ -198,7 +198,11 @@ __device__ __forceinline__ void ntt_round8(uint4* s_lo, uint4* s_hi, const uint4
   for (int k = 0; k < 8; k++) st_planes(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c, x[k]);
 }
 
-__global__ void __launch_bounds__(256, 2) k_ntt_pass(PassParams p) {
+#ifndef PB_NTT_THREADS
+#define PB_NTT_THREADS 256
+#define PB_NTT_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(PassParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t B = 1u << p.log_b, CC = 1u << p.log_cc, TE = B << p.log_cc;
   uint4* s_lo = reinterpret_cast<uint4*>(smem_raw);
@@ -300,7 +304,10 @@ struct NttPlan {
 };
 
 static const int kMaxLogB = 11;    // up to 2048-point tiles
-static const int kTileLog = 11;    // aim for 2048 elements (64 KiB) per tile: CC = 2048 / B adjacent columns
+#ifndef PB_NTT_TILE_LOG
+#define PB_NTT_TILE_LOG 11
+#endif
+static const int kTileLog = PB_NTT_TILE_LOG;    // aim for 2048 elements (64 KiB) per tile: CC = 2048 / B adjacent columns
 
 static size_t pass_smem_bytes(int log_b, int log_cc) {
   size_t B = (size_t)1 << log_b, TE = B << log_cc, TW = B > 1 ? B / 2 : 1;
@@ -472,7 +479,7 @@ void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool invers
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
     ctx->time_begin(1);
-    k_ntt_pass<<<(unsigned)ps.tiles, 256, smem, ctx->stream>>>(q);
+    k_ntt_pass<<<(unsigned)ps.tiles, PB_NTT_THREADS, smem, ctx->stream>>>(q);
     ctx->time_end(1);
     ctx->launches++;
   }
