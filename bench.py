@@ -99,41 +99,66 @@ def reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons of this rank's GPU sampled during the timed region
+    (B200_PROFILING.md).  In-process NVML (no fork, sub-millisecond queries: spawning nvidia-smi from every
+    rank stalls CUDA calls on a busy 8-GPU box); falls back to nvidia-smi when pynvml is missing."""
+    SMI_Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.period = period
+        self.samples = []  # (sm_mhz, sm_max_mhz, power_w, reasons set)
         self.stop_flag = threading.Event()
+        self.recording = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        return sm, self.sm_max, pw, {name for name, bit in self.BITS if mask & bit}
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.SMI_Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+        f = [x.strip() for x in out.stdout.strip().split(",")]
+        reasons = {name for (name, _), v in zip(self.BITS, f[3:7]) if v.lower().startswith("active")}
+        return float(f[0]), float(f[1]), float(f[2]), reasons
 
     def run(self):
         while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+            if self.recording.is_set():
+                try:
+                    self.samples.append(self._sample_nvml() if self.nvml else self._sample_smi())
+                except Exception:
+                    pass
+            self.stop_flag.wait(self.period if self.nvml else 0.2)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         reasons = set()
         for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
-                "reasons": sorted(reasons)}
+            reasons |= s[3]
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.samples[0][1],
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples),
+                "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -199,20 +224,22 @@ def b200_arm(args):
         e1.synchronize()
         barrier()
         ms = e0.elapsed_time(e1)
+        print("[rank %d] %s: %.2f ms for %d steps" % (rank, getattr(fn, "__name__", "fn"), ms, steps), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local)
+    sampler.start()  # started (and NVML initialised) before the warm-up; records only inside the timed regions
     for _ in range(args.warmup):
         prove_device()
     ref_proof = proof.raw
     prove_host()
     assert proof.raw == ref_proof, "host-buffer and device-buffer paths disagree"
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.recording.set()
     launches0 = ctx.launches
     _lib.check(L.pb200_ctx_timing(ctx.handle, 1))
     ms_dev = timed(prove_device, args.steps)
@@ -224,6 +251,7 @@ def b200_arm(args):
     ntt_ms, ntt_cnt = tot.value, cnt.value
     _lib.check(L.pb200_ctx_timing(ctx.handle, 0))
     ms_e2e = timed(prove_host, args.steps)
+    sampler.recording.clear()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     assert proof.raw == ref_proof
