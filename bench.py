@@ -280,7 +280,12 @@ def b200_arm(args):
             _lib.check(L.pb200_fr_ntt(ctx.handle, vp(y.data_ptr()), vp(y.data_ptr()), log_n, 1))
         ntt_pair()
         ms = timed_local(torch, stream, ntt_pair, 5)
-        comp["fr_ntt_fwd_plus_inv_2^%d" % log_n] = {"ms": ms / 5, "elems_per_s": 2 * n / (ms / 5 * 1e-3)}
+        hbm_peak = measured_peaks()[0]
+        gbs = 128.0 * n / (ms / 5 * 1e-3) / 1e9  # 64 B per element per transform, two transforms
+        comp["fr_ntt_fwd_plus_inv_2^%d" % log_n] = {
+            "ms": ms / 5, "elems_per_s": 2 * n / (ms / 5 * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "modmul_ceiling_frac": (2 * (n / 2 * log_n + n) / (ms / 5 * 1e-3)) / 65.4e9}}
         ident = ctypes.c_int()
         out = ctypes.create_string_buffer(64)
 
@@ -288,7 +293,10 @@ def b200_arm(args):
             _lib.check(L.pb200_srs_commit_coeffs(ctx.handle, setup._srs, vp(x.data_ptr()), n, 0, out, ctypes.byref(ident)))
         commit()
         ms = timed_local(torch, stream, commit, 5)
-        comp["g1_msm_fixed_base_2^%d" % log_n] = {"ms": ms / 5, "points_per_s": n / (ms / 5 * 1e-3)}
+        gbs = 96.0 * n / (ms / 5 * 1e-3) / 1e9  # 64 B point + 32 B scalar
+        comp["g1_msm_fixed_base_2^%d" % log_n] = {
+            "ms": ms / 5, "points_per_s": n / (ms / 5 * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}}
 
     if rank != 0:
         if world > 1:
