@@ -442,6 +442,8 @@ Context::Context() {}
 
 Context::~Context() {
   plans.clear();
+  for (auto& e : copy_done) if (e) cudaEventDestroy(e);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 

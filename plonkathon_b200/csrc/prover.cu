@@ -492,9 +492,26 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
   cudaStream_t st = ctx->stream;
   PB_CHECK(n_public <= n, "more public inputs than rows");
   const uint8_t* src[3] = {hA, hB, hC};
-  for (int k = 0; k < 3; k++) {
-    if (wires_on_device) fr_to_mont(ctx, reinterpret_cast<const Fr*>(src[k]), P->lag[k].as<Fr>(), n);
-    else upload_mont(ctx, P->lag[k], src[k], n);
+  if (wires_on_device) {
+    for (int k = 0; k < 3; k++) fr_to_mont(ctx, reinterpret_cast<const Fr*>(src[k]), P->lag[k].as<Fr>(), n);
+  } else {
+    // stage the three wire vectors on a copy stream so the transfers of B and C overlap the conversion and
+    // transform of the previous vector (the copy engine runs beside the SMs)
+    if (!ctx->copy_stream) {
+      PB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (auto& e : ctx->copy_done) PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    PB_CUDA(cudaEventRecord(ctx->copy_done[3], st));  // the destination buffers are free once prior work is done
+    PB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[3], 0));
+    for (int k = 0; k < 3; k++) {
+      PB_CUDA(cudaMemcpyAsync(P->lag[k].p, src[k], n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+      PB_CUDA(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
+    }
+    for (int k = 0; k < 3; k++) {
+      PB_CUDA(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
+      fr_to_mont(ctx, P->lag[k].as<Fr>(), P->lag[k].as<Fr>(), n);
+      ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+    }
   }
   // PI: Lagrange values -public_i (prover.py:57-62)
   PB_CUDA(cudaMemsetAsync(P->pi_lag.p, 0, n * 32, st));
@@ -510,8 +527,9 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
                                           P->sel_lag[Prover::QM].as<Fr>(), P->sel_lag[Prover::QO].as<Fr>(),
                                           P->sel_lag[Prover::QC].as<Fr>(), P->pi_lag.as<Fr>(), n, P->flags.as<uint32_t>());
   ctx->launches++;
-  for (int k = 0; k < 3; k++)
-    ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  if (wires_on_device)
+    for (int k = 0; k < 3; k++)
+      ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
   // public inputs: few of them -> PI is a short combination of cached Lagrange-basis vectors (no transforms);
   // otherwise fall back to interpolating PI like any other column
   P->n_public = n_public;
