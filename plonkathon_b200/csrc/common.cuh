@@ -69,6 +69,8 @@ struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t aux_stream = nullptr;    // independent transforms that overlap the MSM tails on `stream`
+  cudaEvent_t aux_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;   // host->device staging that overlaps compute on `stream`
   cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int sm_count = 148;

@@ -443,6 +443,8 @@ Context::Context() {}
 Context::~Context() {
   plans.clear();
   for (auto& e : copy_done) if (e) cudaEventDestroy(e);
+  for (auto& e : aux_ev) if (e) cudaEventDestroy(e);
+  if (aux_stream) cudaStreamDestroy(aux_stream);
   if (copy_stream) cudaStreamDestroy(copy_stream);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -459,13 +461,24 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
   ntt_run_strided(ctx, in, out, log_n, inverse, n_in, in_scale, out_scale, 1, 0);
 }
 
+void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
+                uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
+
 void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
                      const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add) {
+  ntt_run_on(ctx, ctx->stream, nullptr, in, out, log_n, inverse, n_in, in_scale, out_scale, in_mul, in_add);
+}
+
+// `stream` / `tmp`: run on another stream with a caller-owned pass buffer (2^log_n elements) so that the
+// transform can overlap work on the context's main stream; tmp == nullptr uses the context's scratch.
+void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
+                uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add) {
   NttPlan* plan = get_plan(ctx, log_n, inverse);
   const uint64_t N = (uint64_t)1 << log_n;
   int np = (int)plan->passes.size();
-  Fr* tmp = nullptr;
-  if (np > 1) {
+  const bool main_stream = stream == ctx->stream;
+  if (np > 1 && !tmp) {
+    PB_CHECK(main_stream, "a side-stream transform needs its own pass buffer");
     ctx->scratch[0].ensure((size_t)N * 32);
     tmp = ctx->scratch[0].as<Fr>();
   }
@@ -480,9 +493,9 @@ void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool invers
     q.in_scale = (i == 0) ? in_scale : nullptr;
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
-    ctx->time_begin(1);
-    k_ntt_pass<<<(unsigned)ps.tiles, PB_NTT_THREADS, smem, ctx->stream>>>(q);
-    ctx->time_end(1);
+    if (main_stream) ctx->time_begin(1);
+    k_ntt_pass<<<(unsigned)ps.tiles, PB_NTT_THREADS, smem, stream>>>(q);
+    if (main_stream) ctx->time_end(1);
     ctx->launches++;
   }
   PB_CUDA(cudaGetLastError());

@@ -25,6 +25,26 @@ namespace pb200 {
 
 void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in, const Fr* in_scale,
              const Fr* out_scale);
+void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
+                uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
+
+// Launch the coset extension (to the fixed 4n coset) of coefficient vectors [first, first+count) on the side
+// stream: it depends only on data already produced on the main stream, so it can fill the under-occupied
+// tails of the commitments (bucket reduction, scan, host round trips) that follow on the main stream.
+static void launch_coset_ext_async(Prover* P, int first, int count, int done_event) {
+  Context* ctx = P->ctx;
+  if (!ctx->aux_stream) {
+    PB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->aux_ev) PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  P->aux_tmp.ensure(4 * P->n * 32);
+  PB_CUDA(cudaEventRecord(ctx->aux_ev[3], ctx->stream));          // inputs ready
+  PB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[3], 0));
+  for (int k = first; k < first + count; k++)
+    ntt_run_on(ctx, ctx->aux_stream, P->aux_tmp.as<Fr>(), P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->log_n + 2, false,
+               P->n, P->gpow.as<Fr>(), nullptr, 1, 0);
+  PB_CUDA(cudaEventRecord(ctx->aux_ev[done_event], ctx->aux_stream));
+}
 void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
 Fr fr_from_u64(uint64_t x);
 Fr fr_root_of_unity(int log_n);
@@ -402,6 +422,7 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
   P->tq.alloc(n4 * 32);
   for (int k = 0; k < 5; k++) P->tmp[k].alloc(n * 32);
   P->flags.alloc(64);
+  if (const char* e = getenv("PB200_OVERLAP")) P->overlap = atoi(e) != 0;
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CUDA(cudaGetLastError());
   return P.release();
@@ -546,6 +567,7 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     ntt_run(ctx, P->pi_lag.as<Fr>(), P->coeff[4].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
   }
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
+  if (P->overlap) launch_coset_ext_async(P, 0, 3, 0);
   const Fr* abc[3] = {P->coeff[0].as<Fr>(), P->coeff[1].as<Fr>(), P->coeff[2].as<Fr>()};
   P->commit_batch(abc, 3, n, P->proof.pts[0]);
 }
@@ -578,6 +600,7 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c) {
   ntt_run(ctx, P->lag[3].as<Fr>(), P->coeff[3].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CHECK(total == Fr::one(), "AssertionError: permutation grand product does not close, Z_n != 1 (prover.py:132)");
+  if (P->overlap) launch_coset_ext_async(P, 3, 1, 1);
   P->commit(P->coeff[3].as<Fr>(), n, P->proof.pts[3]);
 }
 
@@ -588,7 +611,11 @@ void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
   cudaStream_t st = ctx->stream;
   P->alpha = fp_to_mont(alpha_c);
   P->fft_cofactor = fp_to_mont(cofactor_c);
-  for (int k = 0; k < (P->pi_sparse ? 4 : 5); k++)
+  if (P->overlap) {  // A, B, C, Z were extended on the side stream during rounds 1 and 2
+    PB_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[0], 0));
+    PB_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));
+  }
+  for (int k = (P->overlap ? 4 : 0); k < (P->pi_sparse ? 4 : 5); k++)
     ntt_run(ctx, P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->log_n + 2, false, n, P->gpow.as<Fr>(), nullptr);
   QuotientArgs q;
   q.pi_cnt = P->pi_sparse ? (int)P->n_public : 0;

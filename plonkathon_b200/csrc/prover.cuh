@@ -38,6 +38,8 @@ struct Prover {
   DevBuf ext[5];         // A B C Z PI on the coset
   DevBuf tq;             // quotient evaluations / coefficients (4n)
   DevBuf tmp[5];
+  DevBuf aux_tmp;        // pass buffer of the side-stream coset transforms (4n)
+  bool overlap = true;   // run the round-3 coset extensions of A, B, C (and Z) beside the round-1/2 MSMs
   DevBuf flags;
   Fr beta, gamma, alpha, fft_cofactor, zeta, v;   // Montgomery
   Fr ev[6];                                      // Montgomery evaluations (round 4)

@@ -1,59 +1,39 @@
-"""Drop-in for the reference's ``transcript.py``: the message dataclasses (transcript.py:8-55) and
+"""Drop-in for the reference's ``transcript.py``: the five message records (transcript.py:8-55) and
 ``Transcript`` (transcript.py:58-123).  The Merlin/STROBE/Keccak machinery is host code inside
-libplonk_b200.so (csrc/transcript.cuh); this class is a thin binding with the reference's method names."""
+libplonk_b200.so (csrc/transcript.cuh); this module binds it and lays the reference's per-round schedule out
+as a table: which fields of a message are absorbed (points as x then y, scalars, all 32-byte big-endian) and
+which challenges are drawn afterwards."""
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass
+from dataclasses import make_dataclass
 
 from . import _lib
 from .curve import Scalar
 
+# round -> (message field names in absorption order, kind of those fields, challenge labels drawn afterwards)
+SCHEDULE = {
+    1: (("a_1", "b_1", "c_1"), "point", ("beta", "gamma")),
+    2: (("z_1",), "point", ("alpha", "fft_cofactor")),
+    3: (("t_lo_1", "t_mid_1", "t_hi_1"), "point", ("zeta",)),
+    4: (("a_eval", "b_eval", "c_eval", "s1_eval", "s2_eval", "z_shifted_eval"), "scalar", ("v",)),
+    5: (("W_z_1", "W_zw_1"), "point", ("u",)),
+}
 
-@dataclass
-class Message1:
-    a_1: object
-    b_1: object
-    c_1: object
-
-
-@dataclass
-class Message2:
-    z_1: object
-
-
-@dataclass
-class Message3:
-    t_lo_1: object
-    t_mid_1: object
-    t_hi_1: object
+# Message1 .. Message5: plain records with exactly the reference's field names and order
+Message1, Message2, Message3, Message4, Message5 = (
+    make_dataclass("Message%d" % rnd, [(name, object) for name in SCHEDULE[rnd][0]]) for rnd in sorted(SCHEDULE))
 
 
-@dataclass
-class Message4:
-    a_eval: Scalar
-    b_eval: Scalar
-    c_eval: Scalar
-    s1_eval: Scalar
-    s2_eval: Scalar
-    z_shifted_eval: Scalar
-
-
-@dataclass
-class Message5:
-    W_z_1: object
-    W_zw_1: object
-
-
-def _n(x) -> int:
+def _as_int(x) -> int:
     return x.n if hasattr(x, "n") else int(x)
 
 
 class Transcript:
     def __init__(self, label: bytes):
-        h = ctypes.c_void_p()
-        _lib.check(_lib.lib().pb200_transcript_create(label, len(label), ctypes.byref(h)))
-        self._h = h
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().pb200_transcript_create(label, len(label), ctypes.byref(handle)))
+        self._h = handle
 
     def __del__(self):
         try:
@@ -63,62 +43,52 @@ class Transcript:
         except Exception:
             pass
 
-    # MerlinTranscript surface
+    # ---- the MerlinTranscript surface the reference's class inherits (transcript.py:3,58)
     def append_message(self, label: bytes, message: bytes) -> None:
         _lib.check(_lib.lib().pb200_transcript_append_message(self._h, label, len(label), message, len(message)))
 
     def challenge_bytes(self, label: bytes, length: int) -> bytes:
-        out = ctypes.create_string_buffer(length)
-        _lib.check(_lib.lib().pb200_transcript_challenge_bytes(self._h, label, len(label), out, length))
-        return out.raw
+        buf = ctypes.create_string_buffer(length)
+        _lib.check(_lib.lib().pb200_transcript_challenge_bytes(self._h, label, len(label), buf, length))
+        return buf.raw
 
-    # transcript.py:59-75
-    def append(self, label: bytes, item: bytes) -> None:
-        self.append_message(label, item)
+    # ---- transcript.py:59-75
+    append = append_message
 
-    def append_scalar(self, label: bytes, item):
-        self.append_message(label, _n(item).to_bytes(32, "big"))
+    def append_scalar(self, label: bytes, item) -> None:
+        self.append_message(label, _as_int(item).to_bytes(32, "big"))
 
-    def append_point(self, label: bytes, item):
-        self.append_message(label, _n(item[0]).to_bytes(32, "big"))
-        self.append_message(label, _n(item[1]).to_bytes(32, "big"))
+    def append_point(self, label: bytes, item) -> None:
+        for coordinate in (item[0], item[1]):  # the identity (None) is unsupported, as in the reference
+            self.append_message(label, _as_int(coordinate).to_bytes(32, "big"))
 
     def get_and_append_challenge(self, label: bytes) -> Scalar:
+        """255 squeezed bytes as a big-endian integer mod r, redrawn while zero, then re-absorbed under the
+        same label -- all inside the library."""
         out = ctypes.create_string_buffer(32)
         _lib.check(_lib.lib().pb200_transcript_get_and_append_challenge(self._h, label, len(label), out))
         return Scalar(int.from_bytes(out.raw, "little"))
 
-    # transcript.py:77-123
-    def round_1(self, message: Message1):
-        self.append_point(b"a_1", message.a_1)
-        self.append_point(b"b_1", message.b_1)
-        self.append_point(b"c_1", message.c_1)
-        beta = self.get_and_append_challenge(b"beta")
-        gamma = self.get_and_append_challenge(b"gamma")
-        return beta, gamma
+    # ---- transcript.py:77-123
+    def _round(self, rnd: int, message):
+        fields, kind, challenges = SCHEDULE[rnd]
+        absorb = self.append_point if kind == "point" else self.append_scalar
+        for name in fields:
+            absorb(name.encode(), getattr(message, name))
+        drawn = tuple(self.get_and_append_challenge(c.encode()) for c in challenges)
+        return drawn if len(drawn) > 1 else drawn[0]
 
-    def round_2(self, message: Message2):
-        self.append_point(b"z_1", message.z_1)
-        alpha = self.get_and_append_challenge(b"alpha")
-        fft_cofactor = self.get_and_append_challenge(b"fft_cofactor")
-        return alpha, fft_cofactor
+    def round_1(self, message):
+        return self._round(1, message)
 
-    def round_3(self, message: Message3):
-        self.append_point(b"t_lo_1", message.t_lo_1)
-        self.append_point(b"t_mid_1", message.t_mid_1)
-        self.append_point(b"t_hi_1", message.t_hi_1)
-        return self.get_and_append_challenge(b"zeta")
+    def round_2(self, message):
+        return self._round(2, message)
 
-    def round_4(self, message: Message4):
-        self.append_scalar(b"a_eval", message.a_eval)
-        self.append_scalar(b"b_eval", message.b_eval)
-        self.append_scalar(b"c_eval", message.c_eval)
-        self.append_scalar(b"s1_eval", message.s1_eval)
-        self.append_scalar(b"s2_eval", message.s2_eval)
-        self.append_scalar(b"z_shifted_eval", message.z_shifted_eval)
-        return self.get_and_append_challenge(b"v")
+    def round_3(self, message):
+        return self._round(3, message)
 
-    def round_5(self, message: Message5):
-        self.append_point(b"W_z_1", message.W_z_1)
-        self.append_point(b"W_zw_1", message.W_zw_1)
-        return self.get_and_append_challenge(b"u")
+    def round_4(self, message):
+        return self._round(4, message)
+
+    def round_5(self, message):
+        return self._round(5, message)
