@@ -143,9 +143,7 @@ class Prover:
     def prove(self, witness) -> Proof:
         """prover.py:51-84."""
         transcript = Transcript(b"plonk")
-        public_vars = self.program.get_public_assignments()
-        self._public = [int(witness[v]) % CURVE_ORDER for v in public_vars]
-        msg_1 = self.round_1(witness)
+        msg_1 = self.round_1(witness)  # also collects the public inputs (prover.py:57-62)
         self.beta, self.gamma = transcript.round_1(msg_1)
         msg_2 = self.round_2()
         self.alpha, self.fft_cofactor = transcript.round_2(msg_2)
@@ -165,8 +163,7 @@ class Prover:
         A = [int(witness[w.L]) % CURVE_ORDER for w in wires]
         B = [int(witness[w.R]) % CURVE_ORDER for w in wires]
         C = [int(witness[w.O]) % CURVE_ORDER for w in wires]
-        if not hasattr(self, "_public"):
-            self._public = [int(witness[v]) % CURVE_ORDER for v in self.program.get_public_assignments()]
+        self._public = [int(witness[v]) % CURVE_ORDER for v in self.program.get_public_assignments()]
         a, b, c = (_as_le_rows(v, n) for v in (A, B, C))
         pub = _as_le_rows(self._public, len(self._public)) if self._public else np.zeros((0, 32), np.uint8)
         out = ctypes.create_string_buffer(192)
