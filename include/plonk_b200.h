@@ -14,6 +14,9 @@
  *     (thread-local).  The Python facade turns errors into exceptions/AssertionErrors matching the
  *     reference's behaviour.
  *   - Work is issued on the context's CUDA stream; calls that return host data synchronise it.
+ *   - A context (and the SRS / prover objects created on it) is not thread-safe: one context per host thread
+ *     and per GPU, like the reference's single-threaded call sequence.  Objects are freed by their _destroy
+ *     call; the caller owns every h_ / d_ buffer it passes in.
  */
 #ifndef PLONK_B200_H
 #define PLONK_B200_H
