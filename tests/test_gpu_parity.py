@@ -503,3 +503,91 @@ def test_polynomial_results_stay_device_resident(pb, setup):
     assert (got[0].n, got[1].n) == O.Setup.from_file(PTAU_HEAD).commit(v)
     c.values = S(pb, [1, 2, 3, 4])  # assigning values drops the device copy
     assert len(c) == 4 and vals(c.fft()) == O.fft([1, 2, 3, 4])
+
+
+# ------------------------------------------------------------------ more of the reference surface
+class _CellProgram:
+    """Program-shaped object (group_order, common_preprocessed_input, wires, get_public_assignments) built from
+    a fixture: every cell gets its own variable name, the witness maps names to the fixture's wire values."""
+
+    def __init__(self, pb, entry, arr):
+        from collections import namedtuple
+        self.group_order = entry["n"]
+        self._W = namedtuple("GateWires", "L R O")
+        self._PK = namedtuple("PK", "group_order QM QL QR QO QC S1 S2 S3")
+        self._P = namedtuple("Poly", "values")
+        self._pb, self._arr = pb, arr
+        self.n_public = len(entry["public"])
+        self.rows = len(arr["A"])
+
+    def common_preprocessed_input(self):
+        a = self._arr
+        return self._PK(self.group_order, *[self._P([self._pb.Scalar(v) for v in a[k]])
+                                            for k in ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3")])
+
+    def wires(self):
+        return [self._W("L%d" % i, "R%d" % i, "O%d" % i) for i in range(self.rows)]
+
+    def get_public_assignments(self):
+        return ["L%d" % i for i in range(self.n_public)]  # public rows carry the variable on the left wire
+
+    def witness(self):
+        a = self._arr
+        w = {}
+        for i in range(self.rows):
+            w["L%d" % i], w["R%d" % i], w["O%d" % i] = a["A"][i], a["B"][i], a["C"][i]
+        return w
+
+
+@pytest.mark.parametrize("name", ["factorization", "poseidon"])
+def test_round_by_round_surface_equals_one_call(pb, setup, name):
+    """Prover(setup, program).prove(witness) -- round_1..5 driven from Python with the Transcript class, as the
+    reference's prove() does -- gives the fixture proof, i.e. the same bytes as the single C call"""
+    import hashlib
+    entry, arr = load_circuit(name)
+    prog = _CellProgram(pb, entry, arr)
+    proof = pb.Prover(setup, prog).prove(prog.witness())
+    assert hashlib.sha256(proof.to_bytes()).hexdigest() == entry["proof_sha256"]
+    flat = proof.flatten()
+    assert list(flat) == list(entry["proof"])  # prover.py:18-35 field order
+
+
+def test_prover_rejects_broken_permutation(pb, setup):
+    """a permutation that does not match the wiring: gates still hold, the grand product does not close
+    (prover.py:132 assert Z_values.pop() == 1)"""
+    entry, arr = load_circuit("factorization")
+    pk = _pk(arr)
+    pk = dict(pk)
+    s1 = list(pk["S1"])
+    s1[1], s1[2] = s1[2], s1[1]
+    s1[3] = (s1[3] + 1) % R
+    pk["S1"] = s1
+    prover = pb.Prover.from_arrays(setup, entry["n"], pk)
+    with pytest.raises(AssertionError, match="grand product"):
+        prover.prove_arrays(arr["A"], arr["B"], arr["C"], ints(entry["public"]))
+
+
+def test_random_small_ntt_and_msm_property(pb):
+    """hypothesis: random sizes / values incl. the field's edge values, NTT and ec_lincomb vs the oracle"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    edge = st.sampled_from([0, 1, 2, R - 1, R - 2, (R - 1) // 2, 1 << 253, (1 << 32) - 1, 1 << 64])
+    elem = st.one_of(edge, st.integers(min_value=0, max_value=R - 1))
+    osetup = O.Setup.from_file(PTAU_HEAD)
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(min_value=0, max_value=7).flatmap(lambda k: st.lists(elem, min_size=1 << k, max_size=1 << k)))
+    def ntt(v):
+        assert vals(pb.Polynomial(S(pb, v), pb.Basis.MONOMIAL).fft()) == O.fft(v)
+        assert vals(pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE).ifft()) == O.ifft(v)
+
+    @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(st.tuples(st.integers(min_value=0, max_value=40), st.one_of(edge, st.integers(-5, R + 5))),
+                    min_size=1, max_size=24))
+    def msm(pairs):
+        pts = osetup.powers_of_x
+        got = pb.ec_lincomb([((pb.FQ(pts[i][0]), pb.FQ(pts[i][1])), s) for i, s in pairs])
+        exp = O.ec_lincomb_naive([(pts[i], s % R) for i, s in pairs])
+        assert (got is None and exp is None) or (got[0].n, got[1].n) == exp
+
+    ntt()
+    msm()
