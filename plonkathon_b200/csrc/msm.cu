@@ -299,12 +299,13 @@ __global__ void __launch_bounds__(128) k_bucket_groups(const G1XYZZ* buckets, ui
                                                        uint32_t n_groups_total, G1XYZZ* out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_groups_total) return;
-  uint32_t groups_per_window = half / gsz;
+  uint32_t groups_per_window = (half + gsz - 1) / gsz;  // the last group of a window may be shorter
   uint32_t w = t / groups_per_window, gi = t % groups_per_window;
   uint32_t lo = gi * gsz;
+  uint32_t len = min(gsz, half - lo);
   const G1XYZZ* base = buckets + (uint64_t)w * half + lo;
   G1XYZZ acc = G1XYZZ::identity(), sum = G1XYZZ::identity();
-  for (int k = (int)gsz - 1; k >= 0; k--) {
+  for (int k = (int)len - 1; k >= 0; k--) {
     G1XYZZ bk = base[k];
     g1_add(acc, bk);
     g1_add(sum, acc);
@@ -478,8 +479,20 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   counts.ensure((size_t)g.nb * 4);
   offsets.ensure((size_t)(g.nb + 1) * 4);
   buckets.ensure((size_t)g.nb * sizeof(G1XYZZ));
+  // group size of the bucket reduction: at least 32 buckets per thread, and large enough that all groups of
+  // the launch are resident at once (the kernel holds 256 threads per SM; a 1.3-wave grid costs two waves)
   uint32_t gsz = g.half >= 32 ? 32 : g.half;
-  uint32_t n_groups = g.nb / gsz;
+  {
+    uint64_t resident = (uint64_t)ctx->sm_count * 256;
+    uint32_t fit = (uint32_t)(((uint64_t)g.nb + resident - 1) / resident);
+    if (fit > gsz && fit <= 2 * gsz) {
+      // keep the groups from straddling windows: choose the per-window count first
+      uint32_t per_window = (uint32_t)(resident / n_windows_out);
+      gsz = (g.half + per_window - 1) / per_window;
+    }
+  }
+  uint32_t groups_per_window = (g.half + gsz - 1) / gsz;
+  uint32_t n_groups = groups_per_window * n_windows_out;
   groups.ensure(((size_t)n_groups + (size_t)n_windows_out * 1024) * sizeof(G1XYZZ));
   wsums.ensure((size_t)n_windows_out * sizeof(G1XYZZ) + 8192 * 4);
 
@@ -521,7 +534,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   k_bucket_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(buckets.as<G1XYZZ>(), g.half, gsz, n_groups,
                                                          groups.as<G1XYZZ>());
   {
-    uint32_t per = g.half / gsz;                       // group results per window
+    uint32_t per = groups_per_window;                  // group results per window
     uint32_t mid = per > 128 ? (per + 127) / 128 : 1;  // first-level blocks per window
     G1XYZZ* level1 = groups.as<G1XYZZ>() + n_groups;
     if (mid > 1) {
