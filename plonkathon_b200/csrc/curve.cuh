@@ -146,6 +146,37 @@ PB_HD void g1_add(G1XYZZ& acc, const G1XYZZ& q) {
   acc.ZZZ = fp_mul(fp_mul(acc.ZZZ, q.ZZZ), PPP);
 }
 
+// acc += q with select-based handling of identity operands (one instruction stream for all lanes, so two
+// independent additions can be interleaved by the compiler); only the rare P == +-Q cases branch.
+PB_HD void g1_add_uniform(G1XYZZ& acc, const G1XYZZ& q) {
+  const bool a_inf = acc.is_inf(), q_inf = q.is_inf();
+  Fq U1 = fp_mul(acc.X, q.ZZ);
+  Fq U2 = fp_mul(q.X, acc.ZZ);
+  Fq S1 = fp_mul(acc.Y, q.ZZZ);
+  Fq S2 = fp_mul(q.Y, acc.ZZZ);
+  Fq Pd = fp_sub(U2, U1);
+  Fq Rd = fp_sub(S2, S1);
+  if (!a_inf && !q_inf && Pd.is_zero()) {
+    if (Rd.is_zero()) g1_double(acc);
+    else acc = G1XYZZ::identity();
+    return;
+  }
+  Fq PP = fp_sqr(Pd);
+  Fq PPP = fp_mul(Pd, PP);
+  Fq Q = fp_mul(U1, PP);
+  Fq X3 = fp_sub(fp_sub(fp_sqr(Rd), PPP), fp_dbl(Q));
+  Fq Y3 = fp_sub(fp_mul(Rd, fp_sub(Q, X3)), fp_mul(S1, PPP));
+  Fq ZZ3 = fp_mul(fp_mul(acc.ZZ, q.ZZ), PP);
+  Fq ZZZ3 = fp_mul(fp_mul(acc.ZZZ, q.ZZZ), PPP);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc.X.v[i] = q_inf ? acc.X.v[i] : (a_inf ? q.X.v[i] : X3.v[i]);
+    acc.Y.v[i] = q_inf ? acc.Y.v[i] : (a_inf ? q.Y.v[i] : Y3.v[i]);
+    acc.ZZ.v[i] = q_inf ? acc.ZZ.v[i] : (a_inf ? q.ZZ.v[i] : ZZ3.v[i]);
+    acc.ZZZ.v[i] = q_inf ? acc.ZZZ.v[i] : (a_inf ? q.ZZZ.v[i] : ZZZ3.v[i]);
+  }
+}
+
 PB_HD G1Affine g1_neg_affine(const G1Affine& p) {
   G1Affine r;
   r.x = p.x;

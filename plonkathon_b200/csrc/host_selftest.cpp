@@ -68,6 +68,12 @@ int hs_curve_op(int op, const uint32_t* acc_in, const uint32_t* other, int other
       break;
     }
     case 2: g1_double(acc); break;
+    case 5: {
+      G1XYZZ q;
+      memcpy(&q, other, sizeof(q));
+      g1_add_uniform(acc, q);
+      break;
+    }
     case 3: {
       G1Affine p;
       bool inf = g1_to_affine(acc, p);

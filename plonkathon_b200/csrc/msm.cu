@@ -304,11 +304,17 @@ __global__ void __launch_bounds__(128) k_bucket_groups(const G1XYZZ* buckets, ui
   uint32_t lo = gi * gsz;
   uint32_t len = min(gsz, half - lo);
   const G1XYZZ* base = buckets + (uint64_t)w * half + lo;
-  G1XYZZ acc = G1XYZZ::identity(), sum = G1XYZZ::identity();
+  // running sums, software-pipelined: acc_(k-1) = acc_k + B_(k-1) does not depend on sum += acc_k, so the two
+  // additions of an iteration are independent and can be interleaved (select-based adds: one instruction stream)
+  G1XYZZ acc = base[len - 1], sum = G1XYZZ::identity();
   for (int k = (int)len - 1; k >= 0; k--) {
-    G1XYZZ bk = base[k];
-    g1_add(acc, bk);
-    g1_add(sum, acc);
+    G1XYZZ nxt = acc;
+    if (k > 0) {
+      G1XYZZ bk = base[k - 1];
+      g1_add_uniform(nxt, bk);
+    }
+    g1_add_uniform(sum, acc);
+    acc = nxt;
   }
   if (lo) {
     G1XYZZ m = g1_mul_small(acc, lo);

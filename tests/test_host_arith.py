@@ -106,6 +106,9 @@ def test_curve_ops(lib):
                 assert to_affine(lib, out_u) == O.g1_add(a, b)
             lib.hs_curve_op(1, acc, xyzz(lib, b), 0, out)  # full add
             assert to_affine(lib, out) == O.g1_add(a, b)
+            out_u2 = (ctypes.c_uint32 * 32)()
+            lib.hs_curve_op(5, acc, xyzz(lib, b), 0, out_u2)  # select-based full add
+            assert to_affine(lib, out_u2) == O.g1_add(a, b)
         # chains with non-trivial ZZ: ((p+q)+q)+(p+q) etc.
         acc = xyzz(lib, p)
         bb = limbs(mont(q[0]) | (mont(q[1]) << 256), 2)
@@ -118,6 +121,9 @@ def test_curve_ops(lib):
         o3 = (ctypes.c_uint32 * 32)()
         lib.hs_curve_op(1, o2, o1, 0, o3)
         assert to_affine(lib, o3) == O.g1_add(exp, O.g1_add(p, q))
+        o3u = (ctypes.c_uint32 * 32)()
+        lib.hs_curve_op(5, o2, o1, 0, o3u)
+        assert to_affine(lib, o3u) == to_affine(lib, o3)
         o4 = (ctypes.c_uint32 * 32)()
         lib.hs_curve_op(1, o3, o3, 0, o4)  # projective doubling through add
         assert to_affine(lib, o4) == O.g1_double(O.g1_add(exp, O.g1_add(p, q)))
