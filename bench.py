@@ -343,6 +343,7 @@ def b200_arm(args):
                              "products/s of this kernel / 65.4e9 measured peak; traffic is 18x the algorithmic bytes because "
                              "every point is gathered once per window (13) from the fixed-base table: see DESIGN.md"},
         "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "launches": int(ntt_cnt), "avg_launch_ms": ntt_avg_ms,
+                         "note": "main-stream passes only; the coset extensions issued on the side stream are not timed",
                          "share_of_step": ntt_ms / ms_dev if ms_dev else None},
         "components": comp,
         "clocks": sampler.summary(),
