@@ -591,3 +591,24 @@ def test_random_small_ntt_and_msm_property(pb):
 
     ntt()
     msm()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_prove_random_circuits_vs_oracle(pb, seed):
+    """differential test over randomly shaped circuits of the synthetic family: group orders 2^3..2^6, partly
+    filled, 0..3 public inputs -- proof bytes equal the oracle's"""
+    from plonkathon_b200 import synthetic as syn
+    rng = random.Random(1000 + seed)
+    log_n = rng.randrange(3, 7)
+    n = 1 << log_n
+    n_public = rng.randrange(0, 4)
+    fill = rng.choice([1.0, 0.9, 0.6])
+    c = syn.build_circuit(log_n, seed=seed, n_public=n_public, fill=fill)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU + seed, n)
+    raw = pb.Prover.from_arrays(setup, n, pk).prove_arrays(A, B, C, public)
+    S1, S2, S3 = syn.permutation_polys(c.wire_L, c.wire_R, c.wire_O, n, c.n_constraints)
+    opk = O.Preprocessed(n, c.QM, c.QL, c.QR, c.QO, c.QC, S1, S2, S3)
+    osetup = O.Setup([(p[0].n, p[1].n) for p in setup.powers_of_x], None)
+    a, b, cc = c.wires_values()
+    assert raw == O.proof_bytes(O.Prover(osetup, opk).prove(a, b, cc, c.public_values())), (log_n, n_public, fill)
