@@ -360,6 +360,29 @@ def b200_arm(args):
                           "single-threaded)" % (args.cpu_log_n, t, log_n, os.cpu_count() or 0)}
         except Exception as e:  # the bench line must still print
             line["cpu_baseline"] = {"value": None, "unit": "proofs/s", "cores": 1, "kind": "port", "sample": "failed: %r" % e}
+    if not args.no_cpu_baseline:
+        # a competent single-threaded CPU implementation for scale (NOT the reference): the C restatement of the
+        # two cores (oracle/c/plonk_oracle.c) on one host core
+        try:
+            from oracle import c_oracle as CO
+            rs = np.random.default_rng(3)
+            v = rs.integers(0, 1 << 32, size=(1 << 18, 8), dtype=np.uint64).astype(np.uint32)
+            v[:, 7] &= 0x0FFFFFFF
+            t0 = time.perf_counter()
+            CO.fft(v.view(np.uint8).reshape(-1, 32))
+            t_fft = time.perf_counter() - t0
+            m = 1 << 14
+            pts = np.frombuffer(b"".join(p[0].n.to_bytes(32, "little") + p[1].n.to_bytes(32, "little")
+                                         for p in setup.export_points(0, m)), dtype=np.uint8).reshape(m, 64)
+            t0 = time.perf_counter()
+            CO.g1_lincomb(pts, v[:m].view(np.uint8).reshape(-1, 32))
+            t_msm = time.perf_counter() - t0
+            line["cpu_c_restatement_1core"] = {
+                "fr_ntt_2^18": {"s": t_fft, "elems_per_s": (1 << 18) / t_fft},
+                "g1_msm_2^14": {"s": t_msm, "points_per_s": m / t_msm},
+                "note": "oracle/c/plonk_oracle.c, one core; a competent-CPU scale line, not the reference's path"}
+        except Exception as e:
+            line["cpu_c_restatement_1core"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
