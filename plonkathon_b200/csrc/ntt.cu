@@ -7,13 +7,14 @@
 // of the input (x4 extension), multiply-on-store by a per-index table (offset^-i).
 //
 // Decomposition (four-step, generalised to 1..3 passes): n = N1*N2(*N3).  Every pass transforms
-// tiles of B = 2^logB points x CC adjacent "batch" columns held in shared memory (two 16-byte planes
-// so 128-bit shared accesses are conflict-free), bit-reversing on the way in so the in-tile DIT stages
-// leave natural order.  Non-final passes multiply by the inter-pass twiddles w_n^(j*k) from an
-// HBM-resident table laid out exactly like the data (so the access is coalesced and costs no extra
-// modmul), and write in place; the final pass writes transposed, CC x 32 B contiguous per row.
-// The per-pass local twiddles w_B^j are staged into shared memory with one TMA bulk copy
-// (cp.async.bulk + mbarrier).
+// tiles of B = 2^logB points (up to 2048) x CC adjacent "batch" columns -- 2048 elements, 64 KiB -- held in
+// shared memory as two 16-byte planes so 128-bit shared accesses are conflict-free.  The tile is bit-reversed
+// on the way in; the in-tile DIT then runs in register-blocked radix-8 rounds (each thread owns 8 positions and
+// does three radix-2 stages in registers between shared-memory exchanges) and leaves natural order.
+// Non-final passes multiply by the inter-pass twiddles w_n^(j*k) from an HBM-resident table laid out exactly
+// like the data (so the access is coalesced and costs no extra modmul), and write in place; the final pass
+// writes transposed, CC x 32 B contiguous per row.  The per-pass local twiddles w_B^j are staged into shared
+// memory with one TMA bulk copy (cp.async.bulk + mbarrier).
 #include "common.cuh"
 
 namespace pb200 {
