@@ -462,12 +462,12 @@ def test_ntt_2p20_exact_vs_c_oracle(pb, logn):
     assert np.array_equal(_raw_ntt(pb, x, logn, 1).view(np.uint8).reshape(n, 32), C.fft(xb, True))
 
 
-def test_msm_2p18_distinct_points_exact_vs_c_oracle(pb):
-    """BASELINE.json configs[2] family: KZG-style MSM over 2^18 DISTINCT points (structured SRS exported from
-    the device) with uniform scalars, both MSM modes, against the C restatement of curve.py:38-44"""
+def test_msm_2p20_distinct_points_exact_vs_c_oracle(pb):
+    """BASELINE.json configs[2]: KZG G1 MSM over 2^20 DISTINCT points (structured SRS exported from the device)
+    with uniform scalars, both MSM modes, bit-exact against the C restatement of curve.py:38-44"""
     from oracle import c_oracle as C
     from plonkathon_b200 import _lib
-    n = 1 << 18
+    n = 1 << 20
     setup = pb.Setup.generate(TAU, n)
     buf = ctypes.create_string_buffer(64 * n)
     _lib.check(_lib.lib().pb200_srs_export(setup.ctx.handle, setup._srs, buf, 0, n))
