@@ -4,6 +4,7 @@
 #include "field.cuh"
 #include "curve.cuh"
 #include "fieldd.cuh"
+#include "msm_digits.cuh"
 #include <cstring>
 using namespace pb200;
 
@@ -32,6 +33,27 @@ int hs_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_
   }
   if (field == 0) RUN(Fr) else RUN(Fq)
   return 0;
+}
+
+// signed digits of a canonical scalar for window size c: writes W = ceil(256 / c) digits (sign * magnitude) and
+// returns the carry left after the last window (must be 0 for scalars < r)
+int hs_msm_digits(const uint32_t* scalar, uint32_t c, int32_t* digits, uint32_t* n_windows) {
+  MsmGeom g;
+  g.c = c;
+  g.W = (256 + c - 1) / c;
+  g.half = 1u << (c - 1);
+  g.bucket_stride = g.half;
+  g.point_stride = 0;
+  g.nb = g.half * g.W;
+  g.batch = 1;
+  Fr s = ld<Fr>(scalar);
+  DigitWalk dw(&s, 0, 0);
+  for (uint32_t w = 0; w < g.W; w++) {
+    uint32_t neg, d = dw.next(w, g, neg);
+    digits[w] = neg ? -(int32_t)d : (int32_t)d;
+  }
+  *n_windows = g.W;
+  return (int)dw.carry;
 }
 
 // FP64-pipe multiplier: out = a * b * 2^-260 mod p on plain integers a, b < p (8 x u32 limbs in and out)

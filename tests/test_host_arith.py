@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(ROOT, "build", "host_selftest.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(CSRC, "host_selftest.cpp")
-    deps = [src, os.path.join(CSRC, "field.cuh"), os.path.join(CSRC, "curve.cuh"), os.path.join(CSRC, "fieldd.cuh")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
                                "-I", CSRC, "-o", out])
@@ -144,3 +144,21 @@ def test_fp64_pipe_multiplier(lib, field, p):
         out = (ctypes.c_uint32 * 8)()
         assert lib.hs_fieldd_mul(field, limbs(a), limbs(b), out) == 0
         assert unlimbs(out) == a * b * r260_inv % p, (hex(a), hex(b))
+
+
+def test_msm_signed_digit_slicing(lib):
+    """csrc/msm_digits.cuh: for every window size the MSM can pick, the signed digits reconstruct the scalar,
+    stay within [-2^(c-1), 2^(c-1)] and leave no carry -- including the field's edge values"""
+    rng = random.Random(21)
+    scalars = [0, 1, 2, O.R_MOD - 1, O.R_MOD - 2, (1 << 253), (1 << 254) - 1 - ((1 << 254) - O.R_MOD) - 1,
+               (1 << 200) - 1, int("55" * 31, 16), int("aa" * 31, 16) % O.R_MOD] + [rng.randrange(O.R_MOD) for _ in range(60)]
+    for c in range(4, 23):
+        for s_ in scalars:
+            digits = (ctypes.c_int32 * 64)()
+            nw = ctypes.c_uint32(0)
+            carry = lib.hs_msm_digits(limbs(s_), c, digits, ctypes.byref(nw))
+            assert carry == 0, (c, hex(s_))
+            assert nw.value == (256 + c - 1) // c
+            ds = [digits[w] for w in range(nw.value)]
+            assert all(abs(d) <= 1 << (c - 1) for d in ds), (c, hex(s_))
+            assert sum(d << (c * w) for w, d in enumerate(ds)) == s_, (c, hex(s_))
