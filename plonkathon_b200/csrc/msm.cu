@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "msm_digits.cuh"
 
 namespace pb200 {
 
@@ -33,8 +34,6 @@ __device__ __forceinline__ G1Affine ld_affine(const G1Affine* p) {
   r.y.v[4] = d.x; r.y.v[5] = d.y; r.y.v[6] = d.z; r.y.v[7] = d.w;
   return r;
 }
-
-#include "msm_digits.cuh"
 
 // counts[bucket]++ for every non-zero digit
 __global__ void k_msm_histogram(ScalarBatch sb, uint64_t n, int from_mont, MsmGeom g, uint32_t* counts) {
