@@ -162,6 +162,19 @@ int pb200_transcript_challenge_bytes(pb200_transcript* t, const uint8_t* label, 
 int pb200_transcript_get_and_append_challenge(pb200_transcript* t, const uint8_t* label, size_t label_len,
                                               uint8_t* out_le32);
 
+/* ---- Pairing and G2 (host code) ------------------------------------------------
+ * Replaces py_ecc's `b.pairing`, `b.add`/`b.multiply` on G2 as the reference's verifier calls them
+ * (TESTING_verifier_DO_NOT_OPEN.py:148-151, 237-262) and `b.is_on_curve(X2, b.b2)` (setup.py:59).
+ * G1 points: 64 B x||y, G2 points: 128 B x.c0||x.c1||y.c0||y.c1 (the .ptau order, setup.py:53-58), every
+ * coordinate 32-byte little-endian canonical; identity flags are one byte per point (NULL = none).
+ * Points off their curve are an error; membership of the order-r subgroup of G2 is NOT checked. */
+/* *ok = 1 iff  prod_i e(g1_i, g2_i) == 1  in GT */
+int pb200_pairing_check(const uint8_t* h_g1, const uint8_t* h_g1_identity, const uint8_t* h_g2,
+                        const uint8_t* h_g2_identity, unsigned count, int* ok);
+int pb200_g2_mul(const uint8_t* h_point, const uint8_t* h_scalar_le32, uint8_t* h_out, int* is_identity);
+int pb200_g2_add(const uint8_t* h_p, int p_identity, const uint8_t* h_q, int q_identity, uint8_t* h_out,
+                 int* is_identity);
+
 /* ---- micro-benchmarks (bench.py / profiles only) --------------------------------------------- */
 /* runs `iters` dependent Montgomery products per thread over `threads` threads; returns elapsed ms */
 int pb200_bench_modmul(pb200_ctx* ctx, int field /*0 Fr, 1 Fq*/, uint64_t threads, uint32_t iters, float* ms_out);

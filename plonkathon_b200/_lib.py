@@ -77,6 +77,9 @@ def _load():
         "pb200_transcript_append_message": (I, [V, V, ctypes.c_size_t, V, ctypes.c_size_t]),
         "pb200_transcript_challenge_bytes": (I, [V, V, ctypes.c_size_t, V, ctypes.c_size_t]),
         "pb200_transcript_get_and_append_challenge": (I, [V, V, ctypes.c_size_t, V]),
+        "pb200_pairing_check": (I, [V, V, V, V, U, P(I)]),
+        "pb200_g2_mul": (I, [V, V, V, P(I)]),
+        "pb200_g2_add": (I, [V, I, V, I, V, P(I)]),
         "pb200_bench_modmul": (I, [V, I, U64, U, P(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "prover.cuh"
+#include "pairing.cuh"
 #include "transcript.cuh"
 
 namespace pb200 {
@@ -460,6 +461,71 @@ int pb200_transcript_get_and_append_challenge(pb200_transcript* t, const uint8_t
   PB_API_BEGIN
   Fr f = reinterpret_cast<Transcript*>(t)->get_and_append_challenge(std::string((const char*)label, label_len));
   memcpy(out_le32, f.v, 32);
+  PB_API_END
+}
+
+// ---- pairing / G2 (host code, pairing.cuh) ----
+static Fq load_fq_canonical(const uint8_t* h) {
+  Fq a;
+  memcpy(a.v, h, 32);
+  Fq m = Fq::modulus();
+  bool lt = false;
+  for (int i = 7; i >= 0; i--) {
+    if (a.v[i] != m.v[i]) { lt = a.v[i] < m.v[i]; break; }
+  }
+  PB_CHECK(lt, "Fq value not reduced below the modulus");
+  return fp_to_mont(a);
+}
+static G2Affine load_g2(const uint8_t* h, bool inf) {
+  G2Affine q;
+  q.inf = inf;
+  q.x = {load_fq_canonical(h), load_fq_canonical(h + 32)};
+  q.y = {load_fq_canonical(h + 64), load_fq_canonical(h + 96)};
+  PB_CHECK(inf || g2_on_curve(q), "G2 point is not on the twist curve");
+  return q;
+}
+static void store_g2(const G2Affine& q, uint8_t* out, int* is_identity) {
+  *is_identity = q.inf ? 1 : 0;
+  memset(out, 0, 128);
+  if (q.inf) return;
+  const Fq c[4] = {fp_from_mont(q.x.a), fp_from_mont(q.x.b), fp_from_mont(q.y.a), fp_from_mont(q.y.b)};
+  for (int k = 0; k < 4; k++) memcpy(out + 32 * k, c[k].v, 32);
+}
+static const Bn254Pairing& pairing_engine() {
+  static const Bn254Pairing engine;  // constants derived once (thread-safe static initialisation)
+  return engine;
+}
+
+int pb200_pairing_check(const uint8_t* h_g1, const uint8_t* h_g1_identity, const uint8_t* h_g2,
+                        const uint8_t* h_g2_identity, unsigned count, int* ok) {
+  PB_API_BEGIN
+  std::vector<G1Host> ps(count);
+  std::vector<G2Affine> qs(count);
+  const Fq three = fq_small(3);
+  for (unsigned i = 0; i < count; i++) {
+    ps[i].inf = h_g1_identity && h_g1_identity[i];
+    if (!ps[i].inf) {
+      ps[i].x = load_fq_canonical(h_g1 + 64 * i);
+      ps[i].y = load_fq_canonical(h_g1 + 64 * i + 32);
+      PB_CHECK(fp_sqr(ps[i].y) == fp_add(fp_mul(fp_sqr(ps[i].x), ps[i].x), three), "G1 point is not on the curve");
+    }
+    qs[i] = load_g2(h_g2 + 128 * i, h_g2_identity && h_g2_identity[i]);
+  }
+  *ok = pairing_engine().product_is_one(ps, qs) ? 1 : 0;
+  PB_API_END
+}
+int pb200_g2_mul(const uint8_t* h_point, const uint8_t* h_scalar_le32, uint8_t* h_out, int* is_identity) {
+  PB_API_BEGIN
+  G2Affine p = load_g2(h_point, false);
+  uint32_t k[8];
+  memcpy(k, h_scalar_le32, 32);
+  store_g2(g2_mul(p, k), h_out, is_identity);
+  PB_API_END
+}
+int pb200_g2_add(const uint8_t* h_p, int p_identity, const uint8_t* h_q, int q_identity, uint8_t* h_out,
+                 int* is_identity) {
+  PB_API_BEGIN
+  store_g2(g2_add(load_g2(h_p, p_identity != 0), load_g2(h_q, q_identity != 0)), h_out, is_identity);
   PB_API_END
 }
 

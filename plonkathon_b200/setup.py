@@ -5,33 +5,17 @@ window table used by the MSM."""
 from __future__ import annotations
 
 import ctypes
-from dataclasses import dataclass
 from typing import Optional
 
 from . import _lib
-from .curve import Scalar, _pt_bytes, _pt_from
-from .field import CURVE_ORDER, FIELD_MODULUS, FQ
+from .curve import G2, Scalar, _pt_bytes, _pt_from, g2_mul
+from .field import CURVE_ORDER, FIELD_MODULUS, FQ, FQ2
 from .poly import Basis, Polynomial, _log2_exact, scalars_to_bytes
+from .verifier import VerificationKey  # noqa: F401  (re-exported: the reference's setup.py imports it too)
 
 SETUP_FILE_G1_STARTPOS = 80  # setup.py:11
 SETUP_FILE_POWERS_POS = 60  # setup.py:12
 _G2_GEN_X_C0 = 10857046999023057135944570762232829481370756359578518086990519993285655852781
-
-
-@dataclass
-class VerificationKey:
-    """verifier.py:10-37 (fields only; verification itself is out of this library's scope)."""
-    group_order: int
-    Qm: object
-    Ql: object
-    Qr: object
-    Qo: object
-    Qc: object
-    S1: object
-    S2: object
-    S3: object
-    X_2: object
-    w: Scalar
 
 
 class Setup:
@@ -49,12 +33,13 @@ class Setup:
     @classmethod
     def generate(cls, tau: int, n: int, ctx: Optional[_lib.Context] = None, precompute: bool = True):
         """Structured test SRS [tau^i]G, i < n, generated on the GPU (the shipped .ptau stops at 2^11 powers,
-        setup.py:27).  ``powers_of_x`` is materialised lazily; X2 is not available (verification only)."""
+        setup.py:27).  ``powers_of_x`` is materialised lazily; ``X2`` = [tau]_2 comes from the library's host G2
+        arithmetic."""
         self = cls.__new__(cls)
         self._powers = None
         self._n = n
-        self.X2 = None
         self.tau = tau % CURVE_ORDER
+        self.X2 = g2_mul(G2, self.tau)
         self.ctx = ctx or _lib.default_context()
         h = ctypes.c_void_p()
         _lib.check(_lib.lib().pb200_srs_generate(self.ctx.handle, self.tau.to_bytes(32, "little"), n,
@@ -102,7 +87,7 @@ class Setup:
         assert pos >= 0, "G2 section not found"
         enc = contents[pos + 128: pos + 256]
         xv = [int.from_bytes(enc[i:i + 32], "little") * finv % FIELD_MODULUS for i in range(0, 128, 32)]
-        X2 = ((xv[0], xv[1]), (xv[2], xv[3]))
+        X2 = (FQ2(xv[0:2]), FQ2(xv[2:4]))  # curve membership (setup.py:59) is checked by the library on first use
         return cls(powers_of_x, X2, ctx=ctx, precompute=precompute)
 
     def commit(self, values: Polynomial):
@@ -119,6 +104,22 @@ class Setup:
         _lib.check(_lib.lib().pb200_srs_commit_lagrange(
             self.ctx.handle, self._srs, ctypes.c_void_p(d_vals.data_ptr()), _log2_exact(n), out, ctypes.byref(ident)))
         return _pt_from(out.raw, ident.value)
+
+    def verification_key_arrays(self, group_order: int, pk_arrays: dict) -> VerificationKey:
+        """``verification_key`` for circuits that exist only as arrays (``Prover.from_arrays``): QM..S3 as
+        (n,32) uint8 little-endian Lagrange values in host memory."""
+        import numpy as np
+        log_n = _log2_exact(group_order)
+        pts = []
+        for k in ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3"):
+            col = np.ascontiguousarray(pk_arrays[k]).view(np.uint8).reshape(-1, 32)
+            assert col.shape[0] == group_order
+            out = ctypes.create_string_buffer(64)
+            ident = ctypes.c_int(0)
+            _lib.check(_lib.lib().pb200_srs_commit_lagrange_host(
+                self.ctx.handle, self._srs, col.ctypes.data_as(ctypes.c_void_p), log_n, out, ctypes.byref(ident)))
+            pts.append(_pt_from(out.raw, ident.value))
+        return VerificationKey(group_order, *pts, self.X2, Scalar.root_of_unity(group_order))
 
     def verification_key(self, pk) -> VerificationKey:
         """setup.py:75-77."""
