@@ -76,6 +76,7 @@ struct Context {
   int sm_count = 148;
   std::map<int, std::unique_ptr<NttPlan>> plans;  // key: log_n * 2 + inverse
   DevBuf scratch[8];                               // reusable temporaries
+  DevBuf msm_aff[6];                               // batched-affine bucket accumulation (msm.cu)
   uint64_t launches = 0;                           // kernels launched through this context
   // optional per-kernel timing (bench.py roofline): CUDA event pairs on the launching stream
   bool timing = false;

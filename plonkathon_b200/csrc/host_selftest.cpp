@@ -5,6 +5,8 @@
 #include "curve.cuh"
 #include "fieldd.cuh"
 #include "msm_digits.cuh"
+#include "msm_affine.cuh"
+#include <vector>
 #include <cstring>
 using namespace pb200;
 
@@ -107,5 +109,63 @@ int hs_curve_op(int op, const uint32_t* acc_in, const uint32_t* other, int other
   }
   memcpy(out, &acc, sizeof(acc));
   return 0;
+}
+
+// Bucket accumulation by rounds of batched affine additions (msm_affine.cuh), every thread body run in a loop.
+// table: n_pts canonical affine points (16 words each); sorted: entries (index | sign << 31) grouped by bucket;
+// offsets: nb + 1.  out: nb canonical affine points + out_inf flags.  Returns the number of rounds, -1 on bad input.
+int hs_msm_affine_rounds(const uint32_t* table, uint32_t n_pts, const uint32_t* sorted, const uint32_t* offsets,
+                         uint32_t nb, uint32_t B, uint32_t F, uint32_t* out, uint8_t* out_inf) {
+  if (B == 0 || F == 0 || F > 32) return -1;
+  std::vector<G1Affine> tab(n_pts);
+  for (uint32_t i = 0; i < n_pts; i++) {
+    tab[i].x = fp_to_mont(ld<Fq>(table + 16 * i));
+    tab[i].y = fp_to_mont(ld<Fq>(table + 16 * i + 8));
+  }
+  std::vector<uint32_t> off_in(offsets, offsets + nb + 1), off_out(nb + 1);
+  std::vector<G1Affine> cur, nxt;
+  int rounds = 0;
+  bool first = true;
+  for (;;) {
+    uint32_t maxc = 0;
+    for (uint32_t b = 0; b < nb; b++) maxc = std::max(maxc, off_in[b + 1] - off_in[b]);
+    AffineRound a;
+    a.table = tab.data();
+    a.sorted = first ? sorted : nullptr;
+    a.in = first ? nullptr : cur.data();
+    a.off_in = off_in.data();
+    a.nb = nb;
+    a.B = B;
+    if (maxc <= 1) {
+      for (uint32_t b = 0; b < nb; b++) {
+        G1XYZZ r = affine_round_bucket(a, b);
+        G1Affine p;
+        bool inf = g1_to_affine(r, p);
+        out_inf[b] = inf ? 1 : 0;
+        Fq x = fp_from_mont(p.x), y = fp_from_mont(p.y);
+        st(out + 16 * b, x);
+        st(out + 16 * b + 8, y);
+      }
+      return rounds;
+    }
+    off_out[0] = 0;
+    for (uint32_t b = 0; b < nb; b++) off_out[b + 1] = off_out[b] + ((off_in[b + 1] - off_in[b] + 1) >> 1);
+    const uint32_t S = off_out[nb], T = (S + B - 1) / B;
+    nxt.assign(S, G1Affine());
+    std::vector<Fq> prefix(S), prod(T + 3);  // a few spare threads: they must do nothing
+    std::vector<uint32_t> desc(S);
+    a.off_out = off_out.data();
+    a.out = nxt.data();
+    a.prefix = prefix.data();
+    a.desc = desc.data();
+    a.thread_prod = prod.data();
+    for (uint32_t t = 0; t < T + 3; t++) affine_round_forward(a, t);
+    for (uint32_t u = 0; u < (T + F - 1) / F + 2; u++) affine_round_invert(prod.data(), T, F, u);
+    for (uint32_t t = T + 3; t-- > 0;) affine_round_backward(a, t);
+    cur.swap(nxt);
+    off_in = off_out;
+    first = false;
+    rounds++;
+  }
 }
 }

@@ -16,9 +16,11 @@
 //      which has to read the point anyway to feed the Fiat-Shamir transcript.
 // Two modes: "generic" (arbitrary points: W windows x 2^(c-1) buckets) and "fixed-base" (SRS with the
 // window multiples 2^(c*w) * P_i precomputed in HBM: one shared set of 2^(c-1) buckets, no Horner).
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
+#include "msm_affine.cuh"
 #include "msm_digits.cuh"
 
 namespace pb200 {
@@ -194,6 +196,34 @@ __global__ void __launch_bounds__(128) k_msm_seg_accumulate(const G1Affine* poin
     if (v >> 31) p.y = fp_neg(p.y);
     g1_add_mixed_uniform(acc, p);
   }
+}
+
+
+// ---- batched-affine bucket accumulation (msm_affine.cuh holds the thread bodies) ---------------------------------
+__global__ void __launch_bounds__(128) k_aff_forward(AffineRound a) {
+  affine_round_forward(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) k_aff_invert(Fq* prod, const uint32_t* slots_total, uint32_t B, uint32_t F) {
+  const uint32_t n = (uint32_t)(((uint64_t)*slots_total + B - 1) / B);
+  affine_round_invert(prod, n, F, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void __launch_bounds__(128) k_aff_backward(AffineRound a) {
+  affine_round_backward(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+// counts[b] = ceil(size of bucket b / 2): the next round's bucket sizes (scanned into its offsets)
+__global__ void k_aff_half_counts(const uint32_t* off_in, uint32_t nb, uint32_t* counts) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) counts[b] = (off_in[b + 1] - off_in[b] + 1) >> 1;
+}
+__global__ void k_aff_buckets(AffineRound a, G1XYZZ* buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < a.nb) buckets[b] = affine_round_bucket(a, b);
+}
+__global__ void k_max_u32(const uint32_t* v, uint32_t n, uint32_t* out) {
+  uint32_t m = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 struct HeavyItem { uint32_t bucket, own_slot, t0, t1; };
@@ -474,18 +504,90 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   PB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)g.nb * 4, st));
   unsigned blocks = (unsigned)((n + 127) / 128);
   k_msm_histogram<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
-  {
-    uint32_t n_tiles = (g.nb + PB_SCAN_TILE - 1) / PB_SCAN_TILE;
-    PB_CHECK(n_tiles <= 8192, "too many buckets for the scan");
-    uint32_t* tile_sums = reinterpret_cast<uint32_t*>(wsums.as<unsigned char>() + (size_t)n_windows_out * sizeof(G1XYZZ));
+  const uint32_t n_tiles = (g.nb + PB_SCAN_TILE - 1) / PB_SCAN_TILE;
+  PB_CHECK(n_tiles <= 8192, "too many buckets for the scan");
+  uint32_t* tile_sums = reinterpret_cast<uint32_t*>(wsums.as<unsigned char>() + (size_t)n_windows_out * sizeof(G1XYZZ));
+  // exclusive scan of `counts` into `off` (nb + 1 entries); leaves counts zeroed
+  auto scan_counts = [&](uint32_t* off) {
     k_scan_tile_sums<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums);
-    k_scan_tiles<<<1, 256, 0, st>>>(tile_sums, n_tiles, offsets.as<uint32_t>() + g.nb);
-    k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums, offsets.as<uint32_t>());
+    k_scan_tiles<<<1, 256, 0, st>>>(tile_sums, n_tiles, off + g.nb);
+    k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums, off);
+  };
+  bool affine = false;
+  if (const char* e = getenv("PB200_MSM_AFFINE")) affine = atoi(e) != 0;
+  if (entries >= (1ull << PB_AFF_INDEX_BITS)) affine = false;  // slot descriptors carry 29-bit element indices
+  uint32_t* max_count = nullptr;
+  if (affine) {
+    ctx->msm_aff[5].ensure((size_t)(g.nb + 1) * 4 + 16);
+    max_count = ctx->msm_aff[5].as<uint32_t>() + (g.nb + 1);
+    PB_CUDA(cudaMemsetAsync(max_count, 0, 4, st));
+    k_max_u32<<<ctx->sm_count * 4, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, max_count);
+    ctx->launches++;
   }
+  scan_counts(offsets.as<uint32_t>());
   k_msm_scatter<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
                                                      counts.as<uint32_t>(), sorted.as<uint32_t>());
-  // balanced accumulation over fixed segments of L sorted entries
-  {
+  if (affine) {
+    // rounds of batched affine additions (msm_affine.cuh): bucket sizes halve each round
+    uint32_t h_max = 0;
+    PB_CUDA(cudaMemcpyAsync(&h_max, max_count, 4, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    uint32_t rounds = 0;
+    while ((1ull << rounds) < h_max) rounds++;
+    uint32_t B = 32, F = 16;
+    if (const char* e = getenv("PB200_MSM_AFFINE_B")) B = (uint32_t)atoi(e);
+    if (const char* e = getenv("PB200_MSM_AFFINE_F")) F = (uint32_t)atoi(e);
+    PB_CHECK(B >= 1 && B <= 4096 && F >= 1 && F <= 32, "bad PB200_MSM_AFFINE_B / PB200_MSM_AFFINE_F");
+    // upper bounds of the slot counts (the exact ones live on the device): S' <= (S + #non-empty buckets) / 2
+    auto half_bound = [&](uint64_t s_in) { return (s_in + std::min<uint64_t>(g.nb, s_in) + 1) / 2; };
+    const uint64_t s1_bound = half_bound(entries), s2_bound = half_bound(s1_bound);
+    DevBuf& buf_a = ctx->msm_aff[0];
+    DevBuf& buf_b = ctx->msm_aff[1];
+    DevBuf& prefix = ctx->msm_aff[2];
+    DevBuf& desc = ctx->msm_aff[3];
+    DevBuf& tprod = ctx->msm_aff[4];
+    if (rounds >= 1) {
+      buf_a.ensure(s1_bound * sizeof(G1Affine));
+      prefix.ensure(s1_bound * sizeof(Fq));
+      desc.ensure(s1_bound * 4);
+      tprod.ensure(((s1_bound + B - 1) / B) * sizeof(Fq));
+    }
+    if (rounds >= 2) buf_b.ensure(s2_bound * sizeof(G1Affine));
+    uint32_t* off_cur = offsets.as<uint32_t>();
+    uint32_t* off_nxt = ctx->msm_aff[5].as<uint32_t>();
+    AffineRound a;
+    a.table = points;
+    a.sorted = sorted.as<uint32_t>();
+    a.in = nullptr;
+    a.nb = g.nb;
+    a.B = B;
+    a.prefix = prefix.as<Fq>();
+    a.desc = desc.as<uint32_t>();
+    a.thread_prod = tprod.as<Fq>();
+    uint64_t bound = entries;
+    ctx->time_begin(0);
+    for (uint32_t r = 0; r < rounds; r++) {
+      k_aff_half_counts<<<(g.nb + 255) / 256, 256, 0, st>>>(off_cur, g.nb, counts.as<uint32_t>());
+      scan_counts(off_nxt);
+      bound = half_bound(bound);
+      const uint32_t threads = (uint32_t)((bound + B - 1) / B);
+      a.off_in = off_cur;
+      a.off_out = off_nxt;
+      a.out = ((r & 1) ? buf_b : buf_a).as<G1Affine>();
+      k_aff_forward<<<(threads + 127) / 128, 128, 0, st>>>(a);
+      k_aff_invert<<<((threads + F - 1) / F + 127) / 128, 128, 0, st>>>(a.thread_prod, off_nxt + g.nb, B, F);
+      k_aff_backward<<<(threads + 127) / 128, 128, 0, st>>>(a);
+      ctx->launches += 7;
+      a.sorted = nullptr;
+      a.in = a.out;
+      std::swap(off_cur, off_nxt);
+    }
+    a.off_in = off_cur;
+    k_aff_buckets<<<(g.nb + 127) / 128, 128, 0, st>>>(a, buckets.as<G1XYZZ>());
+    ctx->time_end(0);
+    ctx->launches -= 2;  // the fixed "+= 10" below counts accumulate + 2 x stitch; this path has k_aff_buckets only
+  } else {
+    // balanced accumulation over fixed segments of L sorted entries
     const uint32_t L = seg_len;
     const uint32_t n_seg = (uint32_t)((entries + L - 1) / L);
     seg.ensure((size_t)n_seg * 2 * sizeof(G1XYZZ) + (size_t)n_seg * 3 * 4 + (size_t)n_seg * sizeof(HeavyItem) + 16);

@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(ROOT, "build", "host_selftest.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(CSRC, "host_selftest.cpp")
-    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh", "msm_affine.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
                                "-I", CSRC, "-o", out])
@@ -162,3 +162,54 @@ def test_msm_signed_digit_slicing(lib):
             ds = [digits[w] for w in range(nw.value)]
             assert all(abs(d) <= 1 << (c - 1) for d in ds), (c, hex(s_))
             assert sum(d << (c * w) for w, d in enumerate(ds)) == s_, (c, hex(s_))
+
+
+def test_msm_affine_rounds_on_host(lib):
+    """csrc/msm_affine.cuh: the per-thread bodies of the batched-affine bucket accumulation, run round by round on
+    the CPU, against the oracle's affine group law -- bucket shapes 0..37, doubled points, opposite points,
+    identities that travel through later rounds, and every (B, F) blocking incl. ones that split buckets"""
+    rng = random.Random(99)
+    base = [O.g1_multiply(O.G1, rng.randrange(1, O.R_MOD)) for _ in range(24)]
+    table = (ctypes.c_uint32 * (16 * len(base)))()
+    for i, (x, y) in enumerate(base):
+        for k in range(8):
+            table[16 * i + k] = (x >> (32 * k)) & 0xFFFFFFFF
+            table[16 * i + 8 + k] = (y >> (32 * k)) & 0xFFFFFFFF
+    P, N = (lambda i: (i, 0)), (lambda i: (i, 1))  # entry = (table index, negated?)
+    buckets = [
+        [], [P(0)], [P(1), P(2)], [P(3), P(3)], [P(4), N(4)], [P(5), N(5), P(6)], [P(6), P(7), P(8), N(8)],
+        [P(9), N(9), P(10), N(10)], [P(11)] * 7, [N(12)] * 8, [P(13), P(13), N(13), N(13), P(14)],
+        [], [], [P(1), N(1), P(1), N(1), P(1), P(2), N(2), P(3), P(3)],
+    ]
+    for size in (3, 5, 16, 31, 37):
+        buckets.append([(rng.randrange(len(base)), rng.randrange(2)) for _ in range(size)])
+    buckets += [[], [N(23)]]
+    entries, offsets = [], [0]
+    for bk in buckets:
+        entries += [i | (s << 31) for i, s in bk]
+        offsets.append(len(entries))
+    expect = []
+    for bk in buckets:
+        acc = None
+        for i, s in bk:
+            acc = O.g1_add(acc, O.g1_neg(base[i]) if s else base[i])
+        expect.append(acc)
+    nb = len(buckets)
+    sorted_arr = (ctypes.c_uint32 * max(1, len(entries)))(*entries)
+    off_arr = (ctypes.c_uint32 * (nb + 1))(*offsets)
+    for B, F in ((1, 1), (2, 3), (3, 32), (5, 2), (8, 8), (32, 32), (1000, 1)):
+        out = (ctypes.c_uint32 * (16 * nb))()
+        inf = (ctypes.c_uint8 * nb)()
+        rounds = lib.hs_msm_affine_rounds(table, len(base), sorted_arr, off_arr, nb, B, F, out, inf)
+        assert rounds == 6  # ceil(log2(37))
+        for b in range(nb):
+            got = None if inf[b] else (unlimbs(out, 2 * b), unlimbs(out, 2 * b + 1))
+            assert got == expect[b], (B, F, b)
+    # nothing to add at all: zero rounds, buckets read straight from the table with their signs
+    off1 = (ctypes.c_uint32 * 4)(0, 1, 1, 2)
+    ent1 = (ctypes.c_uint32 * 2)(5, 7 | (1 << 31))
+    out = (ctypes.c_uint32 * 48)()
+    inf = (ctypes.c_uint8 * 3)()
+    assert lib.hs_msm_affine_rounds(table, len(base), ent1, off1, 3, 4, 4, out, inf) == 0
+    assert (unlimbs(out, 0), unlimbs(out, 1)) == base[5] and inf[1] == 1
+    assert (unlimbs(out, 4), unlimbs(out, 5)) == O.g1_neg(base[7])
