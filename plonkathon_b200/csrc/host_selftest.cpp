@@ -116,7 +116,7 @@ int hs_curve_op(int op, const uint32_t* acc_in, const uint32_t* other, int other
 // offsets: nb + 1.  out: nb canonical affine points + out_inf flags.  Returns the number of rounds, -1 on bad input.
 int hs_msm_affine_rounds(const uint32_t* table, uint32_t n_pts, const uint32_t* sorted, const uint32_t* offsets,
                          uint32_t nb, uint32_t B, uint32_t F, uint32_t* out, uint8_t* out_inf) {
-  if (B == 0 || F == 0 || F > 32) return -1;
+  if (B == 0 || F == 0 || F > 64) return -1;
   std::vector<G1Affine> tab(n_pts);
   for (uint32_t i = 0; i < n_pts; i++) {
     tab[i].x = fp_to_mont(ld<Fq>(table + 16 * i));
@@ -150,18 +150,18 @@ int hs_msm_affine_rounds(const uint32_t* table, uint32_t n_pts, const uint32_t* 
     }
     off_out[0] = 0;
     for (uint32_t b = 0; b < nb; b++) off_out[b + 1] = off_out[b] + ((off_in[b + 1] - off_in[b] + 1) >> 1);
-    const uint32_t S = off_out[nb], T = (S + B - 1) / B;
+    const uint32_t S = off_out[nb], T = affine_round_threads(S, B);
     nxt.assign(S, G1Affine());
-    std::vector<Fq> prefix(S), prod(T + 3);  // a few spare threads: they must do nothing
+    std::vector<Fq> prefix(S), prod(T + 40);  // a spare warp and a bit: those threads must do nothing
     std::vector<uint32_t> desc(S);
     a.off_out = off_out.data();
     a.out = nxt.data();
     a.prefix = prefix.data();
     a.desc = desc.data();
     a.thread_prod = prod.data();
-    for (uint32_t t = 0; t < T + 3; t++) affine_round_forward(a, t);
-    for (uint32_t u = 0; u < (T + F - 1) / F + 2; u++) affine_round_invert(prod.data(), T, F, u);
-    for (uint32_t t = T + 3; t-- > 0;) affine_round_backward(a, t);
+    for (uint32_t t = 0; t < T + 40; t++) affine_round_forward(a, t);
+    for (uint32_t u = 0; u < affine_invert_threads(T, F) + 2; u++) affine_round_invert(prod.data(), T, F, u);
+    for (uint32_t t = T + 40; t-- > 0;) affine_round_backward(a, t);
     cur.swap(nxt);
     off_in = off_out;
     first = false;

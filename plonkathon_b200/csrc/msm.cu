@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(128) k_aff_forward(AffineRound a) {
   affine_round_forward(a, blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(128) k_aff_invert(Fq* prod, const uint32_t* slots_total, uint32_t B, uint32_t F) {
-  const uint32_t n = (uint32_t)(((uint64_t)*slots_total + B - 1) / B);
+  const uint32_t n = affine_round_threads(*slots_total, B);
   affine_round_invert(prod, n, F, blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(128) k_aff_backward(AffineRound a) {
@@ -537,7 +537,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     uint32_t B = 32, F = 16;
     if (const char* e = getenv("PB200_MSM_AFFINE_B")) B = (uint32_t)atoi(e);
     if (const char* e = getenv("PB200_MSM_AFFINE_F")) F = (uint32_t)atoi(e);
-    PB_CHECK(B >= 1 && B <= 4096 && F >= 1 && F <= 32, "bad PB200_MSM_AFFINE_B / PB200_MSM_AFFINE_F");
+    PB_CHECK(B >= 1 && B <= 4096 && F >= 1 && F <= 64, "bad PB200_MSM_AFFINE_B / PB200_MSM_AFFINE_F");
     // upper bounds of the slot counts (the exact ones live on the device): S' <= (S + #non-empty buckets) / 2
     auto half_bound = [&](uint64_t s_in) { return (s_in + std::min<uint64_t>(g.nb, s_in) + 1) / 2; };
     const uint64_t s1_bound = half_bound(entries), s2_bound = half_bound(s1_bound);
@@ -550,7 +550,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
       buf_a.ensure(s1_bound * sizeof(G1Affine));
       prefix.ensure(s1_bound * sizeof(Fq));
       desc.ensure(s1_bound * 4);
-      tprod.ensure(((s1_bound + B - 1) / B) * sizeof(Fq));
+      tprod.ensure((size_t)affine_round_threads((uint32_t)s1_bound, B) * sizeof(Fq));
     }
     if (rounds >= 2) buf_b.ensure(s2_bound * sizeof(G1Affine));
     uint32_t* off_cur = offsets.as<uint32_t>();
@@ -570,12 +570,12 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
       k_aff_half_counts<<<(g.nb + 255) / 256, 256, 0, st>>>(off_cur, g.nb, counts.as<uint32_t>());
       scan_counts(off_nxt);
       bound = half_bound(bound);
-      const uint32_t threads = (uint32_t)((bound + B - 1) / B);
+      const uint32_t threads = affine_round_threads((uint32_t)bound, B);
       a.off_in = off_cur;
       a.off_out = off_nxt;
       a.out = ((r & 1) ? buf_b : buf_a).as<G1Affine>();
       k_aff_forward<<<(threads + 127) / 128, 128, 0, st>>>(a);
-      k_aff_invert<<<((threads + F - 1) / F + 127) / 128, 128, 0, st>>>(a.thread_prod, off_nxt + g.nb, B, F);
+      k_aff_invert<<<(affine_invert_threads(threads, F) + 127) / 128, 128, 0, st>>>(a.thread_prod, off_nxt + g.nb, B, F);
       k_aff_backward<<<(threads + 127) / 128, 128, 0, st>>>(a);
       ctx->launches += 7;
       a.sorted = nullptr;

@@ -10,8 +10,9 @@
 // off_in[b] + 2j + 1, or a copy of the former when that is the bucket's odd last element.
 //
 // One round is three launches:
-//   forward  : thread t owns B consecutive output slots; it multiplies the denominators of its additions into a
-//              running product, storing the product BEFORE each slot (prefix[s]), and classifies each slot (desc[s]);
+//   forward  : thread t owns B output slots (lane-interleaved within its warp's 32 * B consecutive slots); it
+//              multiplies the denominators of its additions into a running product, storing the product BEFORE each
+//              slot (prefix[s]), and classifies each slot (desc[s]);
 //   invert   : the per-thread products are inverted in place, again with Montgomery's trick (F per thread, one
 //              Fermat inversion each) -- two levels, so an inversion is shared by B * F additions;
 //   backward : thread t walks its slots in reverse, peeling 1/denominator off the inverted product, and writes the
@@ -95,9 +96,8 @@ PB_HD G1Affine aff_load(const AffineRound& a, uint32_t e) {
   return p;
 }
 
-// first index i in [0, n) with a[i] > key (n if none)
-PB_HD uint32_t aff_upper_bound(const uint32_t* a, uint32_t n, uint32_t key) {
-  uint32_t lo = 0, hi = n;
+// first index i in [lo, hi) with a[i] > key (hi if none)
+PB_HD uint32_t aff_upper_bound(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t key) {
   while (lo < hi) {
     uint32_t mid = (lo + hi) >> 1;
     if (aff_ld_u32(a + mid) > key) hi = mid; else lo = mid + 1;
@@ -105,31 +105,46 @@ PB_HD uint32_t aff_upper_bound(const uint32_t* a, uint32_t n, uint32_t key) {
   return lo;
 }
 
+// Slot assignment: a warp owns 32 * B consecutive output slots and lane l takes slots w0 + l, w0 + 32 + l, ...,
+// so that at every step the 32 lanes touch 32 consecutive slots (coalesced prefix / desc / out traffic, and
+// consecutive input pairs).  The bucket of a slot is found by bisecting off_out between the buckets of the warp's
+// first and last slot.
+struct AffineSpan {
+  uint32_t w0, w1;      // the warp's slot range [w0, w1)
+  uint32_t lane;
+  uint32_t b_lo, b_hi;  // buckets of slots w0 and w1 - 1
+};
+PB_HD bool affine_span(const AffineRound& a, uint32_t t, AffineSpan& sp) {
+  const uint32_t S = a.off_out[a.nb];
+  const uint64_t w0 = (uint64_t)(t >> 5) * 32 * a.B;
+  if (w0 >= S) return false;
+  sp.w0 = (uint32_t)w0;
+  sp.w1 = (uint32_t)(w0 + 32ull * a.B < S ? w0 + 32ull * a.B : S);
+  sp.lane = t & 31;
+  sp.b_lo = aff_upper_bound(a.off_out, 0, a.nb + 1, sp.w0) - 1;
+  sp.b_hi = aff_upper_bound(a.off_out, sp.b_lo, a.nb + 1, sp.w1 - 1) - 1;
+  return true;
+}
+// number of threads that own a product this round (all lanes of every warp with at least one slot)
+PB_HD uint32_t affine_round_threads(uint32_t S, uint32_t B) {
+  return (uint32_t)(((uint64_t)S + 32ull * B - 1) / (32ull * B)) * 32;
+}
+
 // ---- forward pass of thread t -------------------------------------------------------------------------------
 PB_HD void affine_round_forward(const AffineRound& a, uint32_t t) {
-  const uint32_t S = a.off_out[a.nb];
-  const uint64_t s0_64 = (uint64_t)t * a.B;
-  if (s0_64 >= S) return;
-  const uint32_t s0 = (uint32_t)s0_64;
-  const uint32_t s1 = (uint32_t)(s0_64 + a.B < S ? s0_64 + a.B : S);
-  uint32_t b = aff_upper_bound(a.off_out, a.nb + 1, s0) - 1;  // off_out[b] <= s0 < off_out[b+1]
-  uint32_t out_lo = aff_ld_u32(a.off_out + b), out_hi = aff_ld_u32(a.off_out + b + 1);
-  uint32_t in_lo = aff_ld_u32(a.off_in + b), in_cnt = aff_ld_u32(a.off_in + b + 1) - in_lo;
+  AffineSpan sp;
+  if (!affine_span(a, t, sp)) return;
   Fq acc = Fq::one();
-  for (uint32_t s = s0; s < s1; s++) {
-    while (out_hi <= s) {  // next non-empty bucket
-      b++;
-      out_lo = out_hi;
-      out_hi = aff_ld_u32(a.off_out + b + 1);
-      in_lo = aff_ld_u32(a.off_in + b);
-      in_cnt = aff_ld_u32(a.off_in + b + 1) - in_lo;
-    }
-    const uint32_t j = s - out_lo;
+  uint32_t b = sp.b_lo;
+  for (uint32_t s = sp.w0 + sp.lane; s < sp.w1; s += 32) {
+    b = aff_upper_bound(a.off_out, b + 1, sp.b_hi + 1, s) - 1;  // off_out[b] <= s < off_out[b+1]
+    const uint32_t j = s - aff_ld_u32(a.off_out + b);
+    const uint32_t in_lo = aff_ld_u32(a.off_in + b), in_cnt = aff_ld_u32(a.off_in + b + 1) - in_lo;
     const uint32_t e0 = in_lo + 2 * j;
     uint32_t kind = PB_AFF_COPY;
     if (2 * j + 1 < in_cnt) {
       Fq x1 = aff_load_x(a, e0), x2 = aff_load_x(a, e0 + 1);
-      Fq d;
+      Fq d = Fq::one();
       if (aff_is_identity_x(x1)) {
         kind = PB_AFF_TAKE_Q;
       } else if (aff_is_identity_x(x2)) {
@@ -156,35 +171,42 @@ PB_HD void affine_round_forward(const AffineRound& a, uint32_t t) {
   a.thread_prod[t] = acc;
 }
 
-// ---- in-place inversion of the per-thread products: thread u owns F consecutive entries (F <= 32) ----------------
+// ---- in-place inversion of the per-thread products ------------------------------------------------------------------
+// U = ceil(n / F) threads; thread u owns entries u, u + U, u + 2U, ... (at most F <= 64 of them: neighbouring
+// threads touch neighbouring entries).  All of a thread's entries are fetched before the product chain starts, so
+// the loads overlap instead of each waiting in front of a multiplication.
+PB_HD uint32_t affine_invert_threads(uint32_t n, uint32_t F) { return (n + F - 1) / F; }
 PB_HD void affine_round_invert(Fq* prod, uint32_t n, uint32_t F, uint32_t u) {
-  const uint64_t lo64 = (uint64_t)u * F;
-  if (lo64 >= n) return;
-  const uint32_t lo = (uint32_t)lo64;
-  const uint32_t cnt = n - lo < F ? n - lo : F;
-  Fq pref[32];
+  const uint32_t U = affine_invert_threads(n, F);
+  if (u >= U) return;
+  Fq val[64], pref[64];
+  uint32_t cnt = 0;
+  for (uint32_t k = 0; k < F; k++) {
+    const uint64_t i = (uint64_t)k * U + u;
+    if (i >= n) break;
+    val[k] = prod[i];
+    cnt = k + 1;
+  }
   Fq run = Fq::one();
   for (uint32_t k = 0; k < cnt; k++) {
     pref[k] = run;
-    run = fp_mul(run, prod[lo + k]);
+    run = fp_mul(run, val[k]);
   }
   Fq inv = fp_inv(run);
   for (uint32_t k = cnt; k-- > 0;) {
-    Fq v = prod[lo + k];
-    prod[lo + k] = fp_mul(inv, pref[k]);
-    inv = fp_mul(inv, v);
+    prod[(uint64_t)k * U + u] = fp_mul(inv, pref[k]);
+    inv = fp_mul(inv, val[k]);
   }
 }
 
 // ---- backward pass of thread t ------------------------------------------------------------------------------
 PB_HD void affine_round_backward(const AffineRound& a, uint32_t t) {
-  const uint32_t S = a.off_out[a.nb];
-  const uint64_t s0_64 = (uint64_t)t * a.B;
-  if (s0_64 >= S) return;
-  const uint32_t s0 = (uint32_t)s0_64;
-  const uint32_t s1 = (uint32_t)(s0_64 + a.B < S ? s0_64 + a.B : S);
+  AffineSpan sp;
+  if (!affine_span(a, t, sp)) return;
+  if (sp.w0 + sp.lane >= sp.w1) return;
   Fq inv = a.thread_prod[t];  // 1 / (product of this thread's denominators)
-  for (uint32_t s = s1; s-- > s0;) {
+  const uint32_t last = sp.w0 + sp.lane + ((sp.w1 - 1 - sp.w0 - sp.lane) & ~31u);  // this lane's last slot
+  for (uint32_t s = last;; s -= 32) {
     const uint32_t dsc = a.desc[s];
     const uint32_t e0 = dsc & PB_AFF_INDEX_MASK, kind = dsc >> PB_AFF_INDEX_BITS;
     G1Affine r;
@@ -212,6 +234,7 @@ PB_HD void affine_round_backward(const AffineRound& a, uint32_t t) {
       r = aff_load(a, e0);
     }
     a.out[s] = r;
+    if (s < sp.w0 + 32 + sp.lane) break;
   }
 }
 

@@ -197,7 +197,7 @@ def test_msm_affine_rounds_on_host(lib):
     nb = len(buckets)
     sorted_arr = (ctypes.c_uint32 * max(1, len(entries)))(*entries)
     off_arr = (ctypes.c_uint32 * (nb + 1))(*offsets)
-    for B, F in ((1, 1), (2, 3), (3, 32), (5, 2), (8, 8), (32, 32), (1000, 1)):
+    for B, F in ((1, 1), (2, 3), (3, 64), (5, 2), (8, 8), (32, 32), (1000, 1)):
         out = (ctypes.c_uint32 * (16 * nb))()
         inf = (ctypes.c_uint8 * nb)()
         rounds = lib.hs_msm_affine_rounds(table, len(base), sorted_arr, off_arr, nb, B, F, out, inf)
