@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--cpu-log-n", type=int, default=8, help="size of the bounded CPU sample (2^k gates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip verifying the benchmarked proof (untimed)")
     return ap.parse_args()
 
 
@@ -256,6 +257,19 @@ def b200_arm(args):
     sampler.join(timeout=2)
     assert proof.raw == ref_proof
 
+    # outside every timed region: the proof that was timed is a valid proof -- the product's verifier (GPU linear
+    # combinations + the BN254 pairing against X2 = [tau]_2) accepts it and rejects a tampered copy
+    verified = None
+    if rank == 0 and not args.no_verify:
+        vk = setup.verification_key_arrays(n, pk)
+        pf = pb.Proof.from_bytes(ref_proof)
+        pub_ints = [int(x) for x in public]
+        bad = bytearray(ref_proof)
+        bad[32 * 14 + 31] ^= 1  # lowest bit of a_eval
+        verified = bool(vk.verify_proof(n, pf, pub_ints) and vk.verify_proof_unoptimized(n, pf, pub_ints)
+                        and not vk.verify_proof(n, pb.Proof.from_bytes(bytes(bad)), pub_ints))
+        assert verified, "the benchmarked proof does not verify"
+
     shard_ms = shard_wall_ms = None
     if world > 1:
         # one proof across all GPUs: point-sharded commitments, one NCCL allgather per round (parallel.py)
@@ -333,6 +347,7 @@ def b200_arm(args):
         "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": 3 * n * 32 + 32 * len(public),
                 "d2h_bytes_per_step": 768, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "proof_verified": verified,
         "roofline": {"bound": "hbm", "kernel": "k_msm_seg_accumulate", "achieved": achieved, "peak": hbm_gbs,
                      "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": 96.0 * points_per_launch,
