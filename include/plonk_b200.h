@@ -100,6 +100,11 @@ int pb200_srs_create(pb200_ctx* ctx, const uint8_t* h_points, uint64_t n, int pr
  * the 2^20 / 2^22 configurations need more powers than the reference's shipped .ptau holds
  * (setup.py:27 reads 2^11).  h_tau: canonical 32-byte Fr. */
 int pb200_srs_generate(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out);
+/* the same for the Lagrange basis of the size-n domain (n a power of two): points
+ * [L_i(tau)]G, i < n -- what section 12 of a snarkjs .ptau holds for the ceremony's tau.  Against such an SRS
+ * Setup.commit(values) (setup.py:66-72) is ONE MSM over the values, with no inverse transform:
+ * pb200_srs_commit_coeffs / _host with the LAGRANGE values in place of coefficients. */
+int pb200_srs_generate_lagrange(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out);
 /* copy `count` points starting at `first` back to the host (canonical x||y) */
 int pb200_srs_export(pb200_ctx* ctx, pb200_srs* srs, uint8_t* h_points, uint64_t first, uint64_t count);
 void pb200_srs_destroy(pb200_srs* srs);
@@ -113,6 +118,9 @@ int pb200_srs_commit_lagrange_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t
 /* MSM of m coefficients (monomial basis) with the first m powers. */
 int pb200_srs_commit_coeffs(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m, int coeffs_montgomery,
                             uint8_t* h_out_xy, int* is_identity);
+/* same from host memory (canonical scalars) */
+int pb200_srs_commit_coeffs_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t* h_coeffs, uint64_t m,
+                                 uint8_t* h_out_xy, int* is_identity);
 
 /* ---- Prover (prover.py:39-306) ---------------------------------------------------------------- */
 /* prover.py:45-49  Prover(setup, program): h_pk = 8 pointers, in the order of CommonPreprocessedInput

@@ -52,11 +52,13 @@ def _load():
         "pb200_g1_msm_host": (I, [V, V, V, U64, V, P(I)]),
         "pb200_srs_create": (I, [V, V, U64, I, P(V)]),
         "pb200_srs_generate": (I, [V, V, U64, I, P(V)]),
+        "pb200_srs_generate_lagrange": (I, [V, V, U64, I, P(V)]),
         "pb200_srs_export": (I, [V, V, V, U64, U64]),
         "pb200_srs_destroy": (None, [V]),
         "pb200_srs_size": (U64, [V]),
         "pb200_srs_commit_lagrange": (I, [V, V, V, U, V, P(I)]),
         "pb200_srs_commit_lagrange_host": (I, [V, V, V, U, V, P(I)]),
+        "pb200_srs_commit_coeffs_host": (I, [V, V, V, U64, V, P(I)]),
         "pb200_srs_commit_coeffs": (I, [V, V, V, U64, I, V, P(I)]),
         "pb200_prover_create": (I, [V, V, U, V, P(V)]),
         "pb200_prover_destroy": (None, [V]),

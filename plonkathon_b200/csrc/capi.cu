@@ -27,6 +27,7 @@ struct Srs;
 Srs* srs_create(Context* ctx, const uint8_t* h_points, uint64_t n, int precompute);
 void srs_destroy(Srs* s);
 Srs* srs_generate(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute);
+Srs* srs_generate_lagrange(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute);
 void srs_export(Context* ctx, Srs* srs, uint8_t* h_points, uint64_t first, uint64_t count);
 void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scalars_mont, uint8_t* out_xy, int* is_identity);
 uint64_t srs_size(Srs* s);
@@ -313,6 +314,19 @@ int pb200_srs_generate(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int pre
   PB_API_BEGIN
   PB_CHECK(n > 0, "empty SRS");
   *out = reinterpret_cast<pb200_srs*>(srs_generate(C(ctx), load_fr_canonical(h_tau), n, precompute));
+  PB_API_END
+}
+int pb200_srs_generate_lagrange(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out) {
+  PB_API_BEGIN
+  PB_CHECK(n > 0, "empty SRS");
+  *out = reinterpret_cast<pb200_srs*>(srs_generate_lagrange(C(ctx), load_fr_canonical(h_tau), n, precompute));
+  PB_API_END
+}
+int pb200_srs_commit_coeffs_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t* h_coeffs, uint64_t m,
+                                 uint8_t* h_out_xy, int* is_identity) {
+  PB_API_BEGIN
+  HostStage st(C(ctx), h_coeffs, (size_t)m * 32, 0);
+  srs_msm(C(ctx), reinterpret_cast<Srs*>(srs), (const Fr*)st.in.p, m, false, h_out_xy, is_identity);
   PB_API_END
 }
 int pb200_srs_export(pb200_ctx* ctx, pb200_srs* srs, uint8_t* h_points, uint64_t first, uint64_t count) {

@@ -725,8 +725,14 @@ __global__ void __launch_bounds__(128) k_fb_mul(const G1Affine* table, const Fr*
 void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
 static void srs_finish(Context* ctx, Srs* srs, int precompute);
 
-// tau: canonical Fr; generates n powers on the device
-Srs* srs_generate(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute) {
+void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in, const Fr* in_scale,
+             const Fr* out_scale);
+
+// tau: canonical Fr; generates on the device either the n monomial powers [tau^i] G or, with `lagrange`, the
+// Lagrange-basis points [L_i(tau)] G of the domain of size n (n a power of two).  The Lagrange scalars are the
+// inverse NTT of the power vector: sum_j c_j tau^j = sum_i v_i L_i(tau) with c = iNTT(v) gives
+// L_i(tau) = (1/n) sum_j tau^j w^(-ij).
+static Srs* srs_from_tau(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute, bool lagrange) {
   auto srs = std::make_unique<Srs>();
   srs->n = n;
   srs->base.alloc(n * sizeof(G1Affine));
@@ -734,15 +740,30 @@ Srs* srs_generate(Context* ctx, const Fr& tau_canonical, uint64_t n, int precomp
   DevBuf tab_x(32 * 255 * sizeof(G1XYZZ)), tab(32 * 255 * sizeof(G1Affine));
   k_fb_table<<<(32 * 255 + 127) / 128, 128, 0, st>>>(tab_x.as<G1XYZZ>());
   k_batch_to_affine<<<((32 * 255 + 15) / 16 + 127) / 128, 128, 0, st>>>(tab_x.as<G1XYZZ>(), tab.as<G1Affine>(), 32 * 255);
-  DevBuf pw(n * 32), pts(n * sizeof(G1XYZZ));
+  DevBuf pw(n * 32), pts(n * sizeof(G1XYZZ)), lag;
   launch_powers(ctx, pw.as<Fr>(), n, fp_to_mont(tau_canonical), Fr::one());
-  k_fb_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tab.as<G1Affine>(), pw.as<Fr>(), n, pts.as<G1XYZZ>());
+  const Fr* scalars = pw.as<Fr>();
+  if (lagrange) {
+    int log_n = 0;
+    while (((uint64_t)1 << log_n) < n) log_n++;
+    PB_CHECK(((uint64_t)1 << log_n) == n, "the Lagrange basis needs a power-of-two domain");
+    lag.alloc(n * 32);
+    ntt_run(ctx, pw.as<Fr>(), lag.as<Fr>(), log_n, true, n, nullptr, nullptr);
+    scalars = lag.as<Fr>();
+  }
+  k_fb_mul<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tab.as<G1Affine>(), scalars, n, pts.as<G1XYZZ>());
   uint64_t threads = (n + 15) / 16;
   k_batch_to_affine<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(pts.as<G1XYZZ>(), srs->base.as<G1Affine>(), n);
   ctx->launches += 4;
   PB_CUDA(cudaStreamSynchronize(st));
   srs_finish(ctx, srs.get(), precompute);
   return srs.release();
+}
+Srs* srs_generate(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute) {
+  return srs_from_tau(ctx, tau_canonical, n, precompute, false);
+}
+Srs* srs_generate_lagrange(Context* ctx, const Fr& tau_canonical, uint64_t n, int precompute) {
+  return srs_from_tau(ctx, tau_canonical, n, precompute, true);
 }
 
 // copies the (canonical) affine points back to the host

@@ -666,3 +666,61 @@ def test_prove_then_verify_like_reference_test(pb, setup):
     proof = pb.Proof.from_bytes(raw)
     assert vk.verify_proof_unoptimized(8, proof, [60]) and vk.verify_proof(8, proof, [60])
     assert not vk.verify_proof(8, proof, [61])
+
+
+def test_commit_through_ptau_lagrange_section(pb):
+    """with the .ptau's Lagrange-basis points (section 12) Setup.commit is one MSM over the values.
+    Same results as the reference pins for the inverse-transform path: commitment KAT (test.py:23-28) and the
+    snarkjs verification keys of the n = 8 circuits; n = 16 (factorization); sizes without a block fall back."""
+    import os
+    from collections import namedtuple
+    from tests.golden_io import GOLDEN
+    setup = pb.Setup.from_file(PTAU_HEAD)
+    assert setup._lagrange_handle(8) is None  # the committed head of the file stops before section 12
+    setup.load_lagrange_section(open(os.path.join(GOLDEN, "ptau_lagrange_p0_p4.bin"), "rb").read())
+    kat = load_json("circuits.json")["commit_kat"]
+    c = setup.commit(pb.Polynomial(S(pb, ints(kat["lagrange"])), pb.Basis.LAGRANGE))
+    assert setup._lagrange_handle(8) is not None and (c[0].n, c[1].n) == pt(kat["point"])
+    PK = namedtuple("PK", "group_order QM QL QR QO QC S1 S2 S3")
+    cols = ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3")
+    for name in ("basic", "ab_plus_a", "one_public", "prover_test", "factorization"):
+        entry, arr = load_circuit(name)
+        n = entry["n"]
+        vk = setup.verification_key(PK(n, *[pb.Polynomial(S(pb, arr[k]), pb.Basis.LAGRANGE) for k in cols]))
+        for key in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+            got, exp = getattr(vk, key), pt(entry["vk"][key])
+            assert (got is None and exp is None) or (got[0].n, got[1].n) == exp, (name, key)
+        assert setup._lagrange_handle(n) is not None
+        vk2 = setup.verification_key_arrays(n, {k: np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in arr[k]),
+                                                                 dtype=np.uint8).reshape(-1, 32) for k in cols})
+        assert vk2 == vk
+    rng = random.Random(5)
+    v = [rng.randrange(R) for _ in range(32)]  # no 32-point block in the fixture: inverse transform + monomial powers
+    c = setup.commit(pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE))
+    assert setup._lagrange_handle(32) is None and (c[0].n, c[1].n) == O.Setup.from_file(PTAU_HEAD).commit(v)
+
+
+def test_commit_through_generated_lagrange_srs(pb):
+    """the same for a structured test SRS: [L_i(tau)]G generated on the device (inverse NTT of the tau powers, then
+    fixed-base multiplication); commitments equal the inverse-transform path's and the direct evaluation f(tau) G"""
+    n_max = 1 << 12
+    setup = pb.Setup.generate(TAU, n_max)
+    rng = random.Random(6)
+    for n in (8, 256, n_max):
+        v = [rng.randrange(R) for _ in range(n)]
+        v[1] = 0
+        poly = pb.Polynomial(S(pb, v), pb.Basis.LAGRANGE)
+        via_ntt = setup.commit(poly)
+        assert setup.enable_lagrange(n)
+        via_lagrange = setup.commit(poly)
+        assert via_lagrange == via_ntt
+        assert (via_lagrange[0].n, via_lagrange[1].n) == O.g1_multiply(O.G1, O.eval_lagrange_at(v, TAU))
+    from plonkathon_b200 import synthetic as syn
+    c = syn.build_circuit(10, seed=3, n_public=1)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup.disable_lagrange()
+    vk_ntt = setup.verification_key_arrays(1 << 10, pk)
+    assert setup.enable_lagrange(1 << 10)
+    assert setup.verification_key_arrays(1 << 10, pk) == vk_ntt
+    raw = pb.Prover.from_arrays(setup, 1 << 10, pk).prove_arrays(A, B, C, public)
+    assert vk_ntt.verify_proof(1 << 10, pb.Proof.from_bytes(raw), [int(x) for x in public])
