@@ -122,6 +122,8 @@ class ClockSampler(threading.Thread):
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            self._sample_nvml()  # the first queries initialise NVML state lazily and can stall CUDA calls for
+            self._sample_nvml()  # ~100 ms: take that hit here, long before any timed region
         except Exception:
             self.nvml = None
 
@@ -219,13 +221,17 @@ def b200_arm(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        per_step = []
         for _ in range(steps):
+            t_step = time.perf_counter()
             fn()
+            per_step.append(round((time.perf_counter() - t_step) * 1e3, 1))
         e1.record(stream)
         e1.synchronize()
         barrier()
         ms = e0.elapsed_time(e1)
-        print("[rank %d] %s: %.2f ms for %d steps" % (rank, getattr(fn, "__name__", "fn"), ms, steps), file=sys.stderr)
+        print("[rank %d] %s: %.2f ms for %d steps (host clock per step: %s)"
+              % (rank, getattr(fn, "__name__", "fn"), ms, steps, per_step), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -233,14 +239,17 @@ def b200_arm(args):
         return ms
 
     sampler = ClockSampler(local)
+    if os.environ.get("PB200_BENCH_NO_SAMPLER"):  # debugging aid: leaves "clocks" unavailable
+        sampler.nvml, sampler._sample_smi = None, (lambda: (_ for _ in ()).throw(RuntimeError("disabled")))
     sampler.start()  # started (and NVML initialised) before the warm-up; records only inside the timed regions
     for _ in range(args.warmup):
         prove_device()
     ref_proof = proof.raw
-    prove_host()
+    sampler.recording.set()  # sampling is already running during this last untimed step: nothing about it is new
+    prove_host()             # to the driver when the timed region starts
     assert proof.raw == ref_proof, "host-buffer and device-buffer paths disagree"
-
-    sampler.recording.set()
+    torch.cuda.synchronize()
+    sampler.samples.clear()
     launches0 = ctx.launches
     _lib.check(L.pb200_ctx_timing(ctx.handle, 1))
     ms_dev = timed(prove_device, args.steps)
