@@ -21,6 +21,7 @@ import statistics
 import subprocess
 import sys
 import threading
+from concurrent.futures import ThreadPoolExecutor
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -40,6 +41,9 @@ def parse():
     ap.add_argument("--cpu-log-n", type=int, default=8, help="size of the bounded CPU sample (2^k gates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip verifying the benchmarked proof (untimed)")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="proofs in flight per GPU: independent provers (own stream + scratch, shared SRS), one host "
+                         "thread each; a step is one batch of this many proofs")
     return ap.parse_args()
 
 
@@ -194,44 +198,59 @@ def b200_arm(args):
     setup = pb.Setup.generate(TAU, n, ctx=ctx)
     circ = syn.build_circuit(log_n, seed=20260924, n_public=2)
     pk, A, B, C, public = syn.circuit_arrays(circ)
-    prover = pb.Prover.from_arrays(setup, n, pk)
-    setup_s = time.time() - t0
-    pub = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in public), dtype=np.uint8).reshape(-1, 32).copy()
-    # pinned host buffers (e2e) and device-resident copies (value)
-    hA, hB, hC = (torch.from_numpy(x).pin_memory() for x in (A, B, C))
-    dA, dB, dC = (x.cuda(non_blocking=False) for x in (hA, hB, hC))
-    proof = ctypes.create_string_buffer(768)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    K = max(1, args.inflight)
     vp = ctypes.c_void_p
+    pub = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in public), dtype=np.uint8).reshape(-1, 32).copy()
+    # one lane per proof in flight: context (stream, scratch, NTT plans), prover, pinned host buffers (e2e) and
+    # device-resident copies (value) of the wire values, proof buffer.  Lane 0 uses the setup's own context.
+    lanes = []
+    for k in range(K):
+        lctx = ctx if k == 0 else _lib.Context(local)
+        h3 = tuple(torch.from_numpy(x if k == 0 else x.copy()).pin_memory() for x in (A, B, C))
+        lanes.append({"ctx": lctx, "prover": pb.Prover.from_arrays(setup, n, pk, ctx=lctx), "h": h3,
+                      "d": tuple(x.cuda(non_blocking=False) for x in h3), "proof": ctypes.create_string_buffer(768)})
+    setup_s = time.time() - t0
+    prover, proof = lanes[0]["prover"], lanes[0]["proof"]
+    hA, hB, hC = lanes[0]["h"]
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    pool = ThreadPoolExecutor(K) if K > 1 else None
 
-    def prove_device():
-        _lib.check(L.pb200_prover_prove_device(prover._h, vp(dA.data_ptr()), vp(dB.data_ptr()), vp(dC.data_ptr()),
-                                               pub.ctypes.data_as(vp), pub.shape[0], proof))
+    def prove_device(lane=lanes[0]):
+        _lib.check(L.pb200_prover_prove_device(lane["prover"]._h, *[vp(t.data_ptr()) for t in lane["d"]],
+                                               pub.ctypes.data_as(vp), pub.shape[0], lane["proof"]))
 
-    def prove_host():
-        _lib.check(L.pb200_prover_prove(prover._h, vp(hA.data_ptr()), vp(hB.data_ptr()), vp(hC.data_ptr()),
-                                        pub.ctypes.data_as(vp), pub.shape[0], proof))
+    def prove_host(lane=lanes[0]):
+        _lib.check(L.pb200_prover_prove(lane["prover"]._h, *[vp(t.data_ptr()) for t in lane["h"]],
+                                        pub.ctypes.data_as(vp), pub.shape[0], lane["proof"]))
+
+    def run_lanes(fn, steps, active=None):
+        """every active lane proves `steps` times, all lanes concurrently; returns per-lane host milliseconds"""
+        def worker(lane):
+            t_lane = time.perf_counter()
+            for _ in range(steps):
+                fn(lane)
+            return round((time.perf_counter() - t_lane) * 1e3, 1)
+        active = lanes if active is None else active
+        return [worker(active[0])] if len(active) == 1 else list(pool.map(worker, active))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, active=None, name=None):
+        """device time of `steps` steps; a step = one proof on every active lane.  All lane streams are idle when
+        the first event is recorded and again when the second one is (the prove calls return finished proofs)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        per_step = []
-        for _ in range(steps):
-            t_step = time.perf_counter()
-            fn()
-            per_step.append(round((time.perf_counter() - t_step) * 1e3, 1))
+        per_lane = run_lanes(fn, steps, active)
         e1.record(stream)
         e1.synchronize()
         barrier()
         ms = e0.elapsed_time(e1)
-        print("[rank %d] %s: %.2f ms for %d steps (host clock per step: %s)"
-              % (rank, getattr(fn, "__name__", "fn"), ms, steps, per_step), file=sys.stderr)
+        print("[rank %d] %s: %.2f ms for %d steps x %d lanes (host clock per lane: %s)"
+              % (rank, name or getattr(fn, "__name__", "fn"), ms, steps, len(active or lanes), per_lane), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -242,29 +261,32 @@ def b200_arm(args):
     if os.environ.get("PB200_BENCH_NO_SAMPLER"):  # debugging aid: leaves "clocks" unavailable
         sampler.nvml, sampler._sample_smi = None, (lambda: (_ for _ in ()).throw(RuntimeError("disabled")))
     sampler.start()  # started (and NVML initialised) before the warm-up; records only inside the timed regions
-    for _ in range(args.warmup):
-        prove_device()
+    run_lanes(prove_device, args.warmup)
     ref_proof = proof.raw
     sampler.recording.set()  # sampling is already running during this last untimed step: nothing about it is new
-    prove_host()             # to the driver when the timed region starts
-    assert proof.raw == ref_proof, "host-buffer and device-buffer paths disagree"
+    run_lanes(prove_host, 1)  # to the driver when the timed region starts
+    assert all(lane["proof"].raw == ref_proof for lane in lanes), "lanes / host- and device-buffer paths disagree"
     torch.cuda.synchronize()
     sampler.samples.clear()
-    launches0 = ctx.launches
-    _lib.check(L.pb200_ctx_timing(ctx.handle, 1))
+    launches0 = sum(lane["ctx"].launches for lane in lanes)
     ms_dev = timed(prove_device, args.steps)
-    launches = ctx.launches - launches0
+    launches = sum(lane["ctx"].launches for lane in lanes) - launches0
+    ms_e2e = timed(prove_host, args.steps)
+    sampler.recording.clear()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    assert all(lane["proof"].raw == ref_proof for lane in lanes)
+    # per-kernel durations for the roofline: the same `steps` proofs on lane 0 alone with the library's event pairs
+    # around every accumulation launch and NTT pass (alone, so that a duration is the kernel's own and not a share of
+    # an SM array it divides with the other lane's kernels)
+    _lib.check(L.pb200_ctx_timing(ctx.handle, 1))
+    ms_solo = timed(prove_device, args.steps, active=lanes[:1], name="prove_device (one lane, kernel timing)")
     tot, cnt = ctypes.c_double(), ctypes.c_uint64()
     _lib.check(L.pb200_ctx_timing_read(ctx.handle, 0, ctypes.byref(tot), ctypes.byref(cnt)))
     acc_ms, acc_cnt = tot.value, cnt.value
     _lib.check(L.pb200_ctx_timing_read(ctx.handle, 1, ctypes.byref(tot), ctypes.byref(cnt)))
     ntt_ms, ntt_cnt = tot.value, cnt.value
     _lib.check(L.pb200_ctx_timing(ctx.handle, 0))
-    ms_e2e = timed(prove_host, args.steps)
-    sampler.recording.clear()
-    sampler.stop_flag.set()
-    sampler.join(timeout=2)
-    assert proof.raw == ref_proof
 
     # outside every timed region: the proof that was timed is a valid proof -- the product's verifier (GPU linear
     # combinations + the BN254 pairing against X2 = [tau]_2) accepts it and rejects a tampered copy
@@ -288,7 +310,8 @@ def b200_arm(args):
         assert sp.prove_arrays(pA, pB, pC, public) == ref_proof, "sharded proof differs from the single-GPU proof"
         barrier()
         t0 = time.perf_counter()
-        shard_ms = timed(lambda: sp.prove_arrays(pA, pB, pC, public), args.steps) / args.steps
+        shard_ms = timed(lambda lane: sp.prove_arrays(pA, pB, pC, public), args.steps, active=lanes[:1],
+                         name="one proof sharded across the GPUs") / args.steps
         shard_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         del sp
 
@@ -331,7 +354,7 @@ def b200_arm(args):
             "ms": shard_ms, "ms_wall_clock": shard_wall_ms, "proofs_per_s": 1e3 / shard_ms,
             "note": "pinned host buffers; commitments point-sharded with one NCCL allgather per round, transforms replicated"}
     hbm_gbs, peak_src = measured_peaks()
-    proofs = args.steps * world
+    proofs = args.steps * K * world
     value = proofs / (ms_dev * 1e-3)
     e2e = proofs / (ms_e2e * 1e-3)
     # dominant kernel: MSM bucket accumulation.  Algorithmic bytes: 96 B per point (64 B affine point + 32 B
@@ -350,11 +373,15 @@ def b200_arm(args):
         "vs_baseline": None, "dtype": "u256 (BN254 Fr/Fq integers, 8x32-bit Montgomery limbs)", "data": "synthetic",
         "config": {"workload": "PLONK prove (rounds 1-5, 9 KZG commits), synthetic 2^%d-gate circuit, structured "
                                "test SRS [tau^i]G of 2^%d powers" % (log_n, log_n),
-                   "log_n": log_n, "seed": 20260924, "parallelism": "1 proof per GPU (replicas)" if world > 1 else "1 GPU",
+                   "log_n": log_n, "seed": 20260924,
+                   "parallelism": ("%d GPUs, replicas" % world if world > 1 else "1 GPU") + ", %d proofs in flight per GPU" % K,
+                   "step": "one batch of %d independent proofs per GPU (%d prover lanes: own stream and scratch, shared "
+                           "SRS, one host thread each); one lane alone: %.2f ms per proof" % (K, K, ms_solo / args.steps),
+                   "proofs_in_flight_per_gpu": K,
                    "l2": "working set per proof ~3 GB >> 126 MB L2 (no flush needed)",
                    "setup_seconds_untimed": round(setup_s, 1)},
-        "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": 3 * n * 32 + 32 * len(public),
-                "d2h_bytes_per_step": 768, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": K * (3 * n * 32 + 32 * len(public)),
+                "d2h_bytes_per_step": K * 768, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "proof_verified": verified,
         "roofline": {"bound": "hbm", "kernel": "k_msm_seg_accumulate", "achieved": achieved, "peak": hbm_gbs,
@@ -362,13 +389,13 @@ def b200_arm(args):
                      "algorithmic_bytes_per_launch": 96.0 * points_per_launch,
                      "modmul_ceiling_frac": (10.0 * 13 * points_per_launch / (acc_avg_ms * 1e-3)) / 65.4e9,
                      "launches": int(acc_cnt), "avg_launch_ms": acc_avg_ms,
-                     "share_of_step": acc_ms / ms_dev if ms_dev else None,
-                     "note": "integer-pipe bound (ncu: fmaheavy pipe 87% active), not HBM bound; modmul_ceiling_frac = Montgomery "
+                     "share_of_step": acc_ms / ms_solo if ms_solo else None,
+                     "note": "kernel durations from a pass with one lane (see config.step); integer-pipe bound (ncu: fmaheavy pipe 87% active), not HBM bound; modmul_ceiling_frac = Montgomery "
                              "products/s of this kernel / 65.4e9 measured peak; traffic is 18x the algorithmic bytes because "
                              "every point is gathered once per window (13) from the fixed-base table: see DESIGN.md"},
         "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "launches": int(ntt_cnt), "avg_launch_ms": ntt_avg_ms,
                          "note": "main-stream passes only; the coset extensions issued on the side stream are not timed",
-                         "share_of_step": ntt_ms / ms_dev if ms_dev else None},
+                         "share_of_step": ntt_ms / ms_solo if ms_solo else None},
         "components": comp,
         "clocks": sampler.summary(),
     }

@@ -779,6 +779,7 @@ void prover_serialize(const Prover* P, uint8_t* out768) {
 // prover.py:51-84
 void prover_prove(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
                   uint64_t n_public, uint8_t* out768, bool wires_on_device) {
+  PB_CUDA(cudaSetDevice(P->ctx->device));  // the calling host thread may not be the one that created the context
   Transcript tr("plonk");  // prover.py:53
   prover_round1(P, hA, hB, hC, h_public, n_public, wires_on_device);
   tr.append_point_le("a_1", P->proof.pts[0]);

@@ -95,19 +95,21 @@ class Prover:
         self._create(setup, self.group_order, cols)
 
     @classmethod
-    def from_arrays(cls, setup, group_order: int, pk_arrays: dict):
-        """pk_arrays: QM QL QR QO QC S1 S2 S3 -> list of ints or (n,32) uint8 little-endian arrays."""
+    def from_arrays(cls, setup, group_order: int, pk_arrays: dict, ctx=None):
+        """pk_arrays: QM QL QR QO QC S1 S2 S3 -> list of ints or (n,32) uint8 little-endian arrays.
+        ``ctx``: run this prover on another context (stream + scratch) of the same device than the setup's; the SRS
+        is shared read-only, so several provers can be driven concurrently from different host threads."""
         self = cls.__new__(cls)
         self.group_order = group_order
         self.setup = setup
         self.program = None
         self.pk = None
         cols = {k: _as_le_rows(pk_arrays[k], group_order) for k in PK_ORDER}
-        self._create(setup, group_order, cols)
+        self._create(setup, group_order, cols, ctx)
         return self
 
-    def _create(self, setup, n, cols):
-        self.ctx = setup.ctx
+    def _create(self, setup, n, cols, ctx=None):
+        self.ctx = ctx or setup.ctx
         self._log_n = _log2_exact(n)
         keep = [c if isinstance(c, bytes) else c.tobytes() for c in (cols[k] for k in PK_ORDER)]
         arr = (ctypes.c_char_p * 8)(*keep)
