@@ -724,3 +724,26 @@ def test_commit_through_generated_lagrange_srs(pb):
     assert setup.verification_key_arrays(1 << 10, pk) == vk_ntt
     raw = pb.Prover.from_arrays(setup, 1 << 10, pk).prove_arrays(A, B, C, public)
     assert vk_ntt.verify_proof(1 << 10, pb.Proof.from_bytes(raw), [int(x) for x in public])
+
+
+def test_two_prover_lanes_on_one_gpu(pb):
+    """bench.py's throughput mode: two provers on their own contexts (stream + scratch), sharing one SRS, driven from
+    two host threads at the same time -- same bytes as one prover alone, every time"""
+    from concurrent.futures import ThreadPoolExecutor
+    from plonkathon_b200 import _lib, synthetic as syn
+    log_n = 14
+    n = 1 << log_n
+    setup = pb.Setup.generate(TAU, n)
+    circuits = [syn.circuit_arrays(syn.build_circuit(log_n, seed=s, n_public=2)) for s in (11, 12)]
+    alone = [pb.Prover.from_arrays(setup, n, c[0]).prove_arrays(c[1], c[2], c[3], c[4]) for c in circuits]
+    assert alone[0] != alone[1]
+    lanes = [pb.Prover.from_arrays(setup, n, c[0], ctx=_lib.Context(0) if i else None) for i, c in enumerate(circuits)]
+    assert lanes[0].ctx is setup.ctx and lanes[1].ctx is not setup.ctx
+
+    def worker(i):
+        c = circuits[i]
+        return [lanes[i].prove_arrays(c[1], c[2], c[3], c[4]) for _ in range(6)]
+
+    with ThreadPoolExecutor(2) as pool:
+        got = list(pool.map(worker, range(2)))
+    assert got[0] == [alone[0]] * 6 and got[1] == [alone[1]] * 6
