@@ -16,7 +16,7 @@ for n, v in zip(names[i0:i1], vals[i0:i1]):
 with open("profiles/%s_launches_one_proof.md" % tag, "w") as f:
     f.write("# %s -- ncu launch list of one 2^20-gate proof\n\n" % tag)
     f.write("Command (under gpurun): `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "
-            "gpurun_out/r1_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline`\n\n")
+            "gpurun_out/r1_launches.csv python bench.py --inflight 1 --steps 1 --warmup 1 --no-cpu-baseline`\n\n")
     f.write("One proof = the launches between two consecutive `k_gate_check` launches (%d kernels, sum of durations "
             "%.2f ms; per-launch times under ncu are cold-cache and serialised -- compare shares).\n\n" % (i1 - i0, tot / 1e6))
     f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
