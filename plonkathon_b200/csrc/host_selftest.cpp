@@ -6,6 +6,7 @@
 #include "fieldd.cuh"
 #include "msm_digits.cuh"
 #include "msm_affine.cuh"
+#include "modinv.cuh"
 #include <vector>
 #include <cstring>
 using namespace pb200;
@@ -14,7 +15,8 @@ template <class F> static F ld(const uint32_t* p) { F r; memcpy(r.v, p, 32); ret
 template <class F> static void st(uint32_t* p, const F& a) { memcpy(p, a.v, 32); }
 
 extern "C" {
-// op: 0 add, 1 sub, 2 mul, 3 neg, 4 inv, 5 to_mont, 6 from_mont, 7 dbl, 8 sqr ; field: 0 Fr, 1 Fq
+// op: 0 add, 1 sub, 2 mul, 3 neg, 4 inv, 5 to_mont, 6 from_mont, 7 dbl, 8 sqr, 9 inv by safegcd (Montgomery
+// contract of op 4), 10 plain-integer inverse by safegcd ; field: 0 Fr, 1 Fq
 int hs_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
 #define RUN(F)                                                   \
   {                                                              \
@@ -29,6 +31,8 @@ int hs_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_
       case 6: r = fp_from_mont(x); break;                        \
       case 7: r = fp_dbl(x); break;                              \
       case 8: r = fp_sqr(x); break;                              \
+      case 9: r = fp_inv_gcd(x); break;                          \
+      case 10: r = fp_inv_plain_gcd(x); break;                   \
       default: return -1;                                        \
     }                                                            \
     st(out, r);                                                  \

@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(ROOT, "build", "host_selftest.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(CSRC, "host_selftest.cpp")
-    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh", "msm_affine.cuh")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh", "msm_affine.cuh", "modinv.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
                                "-I", CSRC, "-o", out])
@@ -213,3 +213,20 @@ def test_msm_affine_rounds_on_host(lib):
     assert lib.hs_msm_affine_rounds(table, len(base), ent1, off1, 3, 4, 4, out, inf) == 0
     assert (unlimbs(out, 0), unlimbs(out, 1)) == base[5] and inf[1] == 1
     assert (unlimbs(out, 4), unlimbs(out, 5)) == O.g1_neg(base[7])
+
+
+@pytest.mark.parametrize("field,p", [(0, O.R_MOD), (1, O.Q_MOD)])
+def test_safegcd_inverse(lib, field, p):
+    """csrc/modinv.cuh: inversion by batches of 30 Bernstein-Yang division steps on signed 30-bit limbs -- plain
+    integers against pow(x, -1, p), and the Montgomery-form wrapper against the Fermat fp_inv it is meant to replace"""
+    rng = random.Random(40 + field)
+    vals = EDGE + [p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, R256 % p, 1 << 253, (1 << 253) + 1, 3 << 252 if (3 << 252) < p else 5,
+                   (1 << 30) - 1, 1 << 30, (1 << 60) + 1, p - (1 << 30), p - (1 << 200)]
+    vals += [rng.randrange(p) for _ in range(3000)]
+    vals += [rng.randrange(1 << k) for k in range(1, 254, 7) for _ in range(4)]
+    for a in vals:
+        a %= p
+        assert fop(lib, field, 10, a) == (pow(a, -1, p) if a else 0), a
+    for a in vals[:400]:
+        a %= p
+        assert fop(lib, field, 9, a) == fop(lib, field, 4, a), a
