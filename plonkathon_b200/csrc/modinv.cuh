@@ -2,11 +2,11 @@
 // Bernstein-Yang "safegcd" division steps in batches of 30 on signed 30-bit limbs, for the per-round inversion of the
 // batched-affine bucket accumulation (msm_affine.cuh), where the Fermat chain of fp_inv (380 dependent Montgomery
 // products, ~70 k instructions) is the latency that every round waits for (profiles/r01_msm_affine.md).
-// One batch = 30 division steps on the low words (branch-free, ~25 integer instructions per step) that produce a
-// 2x2 transition matrix with entries below 2^30 in magnitude, which is then applied to the full-width (f, g) exactly
-// and to (d, e) modulo p: ~1 k instructions per batch, at most 25 batches for a 256-bit modulus (741 steps bound),
-// 18 for almost every BN254 input (17-19 over 20 000 random ones) -- about a quarter of the Fermat chain's
-// instructions, and no chain of dependent 256-bit multiplications.
+// One batch = 30 division steps on the low words (branch-free; ~40 SASS instructions per step on sm_100a) that produce
+// a 2x2 transition matrix with entries below 2^30 in magnitude, which is then applied to the full-width (f, g) exactly
+// and to (d, e) modulo p: ~1.5 k instructions per batch, at most 25 batches for a 256-bit modulus (741 steps bound),
+// 18 for almost every BN254 input (17-19 over 20 000 random ones): ~28 k instructions per inversion against ~72 k,
+// 66 registers, and no chain of dependent 256-bit multiplications.  Device timing is still to be measured.
 // Host/device code like field.cuh: unit-tested on the CPU against Python's pow(x, -1, p) (tests/test_host_arith.py).
 #pragma once
 #include "field.cuh"
