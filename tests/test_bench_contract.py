@@ -17,7 +17,12 @@ def test_reference_arm_json_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "proofs/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    one = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-log-n", "4", "--cpu-procs", "1"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    single = json.loads(one.stdout.strip().splitlines()[-1])
+    assert single["cpu_baseline"]["cores"] == 1 and 0 < single["value"] <= line["value"] * 1.5
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["vs_baseline"] is None
     assert "workload" in line["config"]
 
