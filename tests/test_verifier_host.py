@@ -131,3 +131,22 @@ def test_verifier_accepts_golden_and_rejects_tampered(name, monkeypatch):
     bad = raw[:k] + ((int.from_bytes(raw[k:k + 32], "big") + 5) % R).to_bytes(32, "big") + raw[k + 32:]
     assert not vk.verify_proof(n, pb.Proof.from_bytes(bad), public)
     assert not vk.verify_proof_unoptimized(n, pb.Proof.from_bytes(bad), public)
+
+
+def test_pairing_entry_point_edge_cases():
+    ok = ctypes.c_int(-1)
+    L = _lib.lib()
+    # empty product is 1
+    _lib.check(L.pb200_pairing_check(None, None, None, None, 0, ctypes.byref(ok)))
+    assert ok.value == 1
+    # identity flags make the coordinate bytes irrelevant (they are not even range-checked for G1)
+    g2 = b"".join(int(c).to_bytes(32, "little") for c in (*pb.G2[0].coeffs, *pb.G2[1].coeffs))
+    _lib.check(L.pb200_pairing_check(b"\xff" * 64, bytes([1]), g2, bytes([0]), 1, ctypes.byref(ok)))
+    assert ok.value == 1
+    # e(P, Q) e(P, -Q) == 1 and the order of the factors does not matter
+    nq = pb.g2_mul(pb.G2, -1)
+    assert pb.pairing_product_is_one([(O.G1, pb.G2), (O.G1, nq)]) and pb.pairing_product_is_one([(O.G1, nq), (O.G1, pb.G2)])
+    # scalars are reduced mod r: [r + 5] Q == [5] Q
+    assert pb.g2_mul(pb.G2, R + 5) == pb.g2_mul(pb.G2, 5) == g2_of(b.multiply(b.G2, 5))
+    with pytest.raises(AssertionError):
+        pb.Proof.from_bytes(b"\x00" * 767)
