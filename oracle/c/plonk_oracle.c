@@ -272,3 +272,48 @@ int oc_g1_lincomb(const uint8_t* points, const uint8_t* scalars, uint64_t n, uin
   free(pts); free(buckets);
   return 0;
 }
+
+/* Structured test SRS for sizes the reference's .ptau does not reach (setup.py:16-22 `powers_of_x` for a known
+ * tau): out[i] = [tau^i] G, i < n, as x || y canonical little-endian.  G = (1, 2).  Fixed-base multiplication
+ * with byte windows (table[w][d] = d * 2^(8w) * G) and one shared inversion per chunk of 1024 points. */
+int oc_g1_powers(const uint8_t* tau32, uint64_t n, uint8_t* out) {
+  ensure_init();
+  jac (*table)[256] = (jac (*)[256])malloc(32 * 256 * sizeof(jac));
+  enum { CH = 1024 };
+  jac* acc = (jac*)malloc(CH * sizeof(jac));
+  fe* pref = (fe*)malloc(CH * sizeof(fe));
+  if (!table || !acc || !pref) return 1;
+  jac base; fe two;
+  base.X = FQ.r1; fe_add(&FQ, &two, &FQ.r1, &FQ.r1); base.Y = two; base.Z = FQ.r1;
+  for (int w = 0; w < 32; w++) {
+    memset(&table[w][0], 0, sizeof(jac));
+    for (int d = 1; d < 256; d++) jac_add(&table[w][d], &table[w][d - 1], &base);
+    for (int k = 0; k < 8; k++) jac_double(&base, &base);
+  }
+  fe tau, tau_m, cur; memcpy(tau.v, tau32, 32); fe_to_mont(&FR, &tau_m, &tau);
+  cur = FR.r1;  /* tau^0 in Montgomery form */
+  for (uint64_t i0 = 0; i0 < n; i0 += CH) {
+    uint64_t cnt = n - i0 < CH ? n - i0 : CH;
+    for (uint64_t k = 0; k < cnt; k++) {
+      fe s; fe_from_mont(&FR, &s, &cur);
+      const uint8_t* sb = (const uint8_t*)s.v;
+      jac a; memset(&a, 0, sizeof a);
+      for (int w = 0; w < 32; w++) if (sb[w]) jac_add(&a, &a, &table[w][sb[w]]);
+      acc[k] = a;  /* never the identity: tau^i != 0 mod r */
+      fe_mul(&FR, &cur, &cur, &tau_m);
+    }
+    fe run = FQ.r1;
+    for (uint64_t k = 0; k < cnt; k++) { pref[k] = run; fe_mul(&FQ, &run, &run, &acc[k].Z); }
+    fe inv; fe_inv(&FQ, &inv, &run);
+    for (uint64_t k = cnt; k-- > 0;) {
+      fe zi, zi2, zi3, x, y, t;
+      fe_mul(&FQ, &zi, &inv, &pref[k]); fe_mul(&FQ, &inv, &inv, &acc[k].Z);
+      fe_mul(&FQ, &zi2, &zi, &zi); fe_mul(&FQ, &zi3, &zi2, &zi);
+      fe_mul(&FQ, &x, &acc[k].X, &zi2); fe_mul(&FQ, &y, &acc[k].Y, &zi3);
+      fe_from_mont(&FQ, &t, &x); memcpy(out + 64 * (i0 + k), t.v, 32);
+      fe_from_mont(&FQ, &t, &y); memcpy(out + 64 * (i0 + k) + 32, t.v, 32);
+    }
+  }
+  free(table); free(acc); free(pref);
+  return 0;
+}

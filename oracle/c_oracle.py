@@ -59,3 +59,15 @@ def eval_lagrange(vals: np.ndarray, x: int) -> int:
     rc = lib().oc_fr_eval_lagrange(_p(v), v.shape[0].bit_length() - 1, _p(xb), _p(out))
     assert rc == 0
     return int.from_bytes(out.tobytes(), "little")
+
+
+def g1_powers(tau: int, n: int) -> np.ndarray:
+    """[tau^i] G for i < n as an (n, 64) uint8 array (x || y canonical little-endian): the structured test SRS."""
+    out = np.zeros((n, 64), dtype=np.uint8)
+    tb = np.frombuffer((int(tau) % R_ORDER).to_bytes(32, "little"), dtype=np.uint8).copy()
+    rc = lib().oc_g1_powers(_p(tb), ctypes.c_uint64(n), _p(out))
+    assert rc == 0
+    return out
+
+
+R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617

@@ -302,7 +302,8 @@ def test_prove_synthetic_vs_oracle(pb, log_n, fill):
 
 def test_prove_2p20_gates_verifies(pb):
     """BASELINE.json's headline size: a 2^20-gate synthetic circuit.  The reference cannot produce a proof
-    at this size (5 h of Python; SRS file holds 2^11 powers), so parity is established end to end by the
+    at this size (5 h of Python; SRS file holds 2^11 powers); parity is established byte for byte against the
+    golden proof of the oracle prover run over the C restatement, and end to end by the
     reference's verification equation (TESTING_verifier_DO_NOT_OPEN.py:39-163) evaluated by the oracle with
     the known tau of the structured SRS, plus independent CPU evaluation of two verification-key
     commitments, plus determinism (two runs, host-buffer and device-buffer paths agree in bench.py)."""
@@ -315,6 +316,14 @@ def test_prove_2p20_gates_verifies(pb):
     prover = pb.Prover.from_arrays(setup, n, pk)
     raw = prover.prove_arrays(A, B, C, public)
     assert prover.prove_arrays(A, B, C, public) == raw
+    # byte for byte against the oracle's proof of the same circuit (tests/golden/make_proof_2p20.py: the oracle prover
+    # over the C restatement of fft / ec_lincomb, ~20 CPU-minutes, committed as a fixture)
+    import json
+    import os
+    from tests.golden_io import GOLDEN
+    rec = json.load(open(os.path.join(GOLDEN, "proof_2p20.json")))
+    assert rec["log_n"] == log_n and rec["seed"] == 7 and [int(x) for x in rec["public"]] == [int(x) for x in public]
+    assert raw.hex() == rec["proof_hex"], "GPU proof differs from the oracle's golden proof at 2^20 gates"
     proof = O.proof_from_bytes(raw)
     for k in ("a_1", "z_1", "t_hi_1", "W_zw_1"):
         assert O.g1_is_on_curve(proof[k])
