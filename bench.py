@@ -314,6 +314,17 @@ def b200_arm(args):
     ntt_ms, ntt_cnt = tot.value, cnt.value
     _lib.check(L.pb200_ctx_timing(ctx.handle, 0))
 
+    # outside every timed region: byte-for-byte against the oracle's golden proof of this very circuit, when the
+    # fixture for this size and seed exists (tests/golden/make_proof_2p20.py; reading a JSON file is not running the
+    # oracle).  Reported, not asserted: the parity gate is the test-suite, the bench only says what it saw.
+    golden_match = None
+    gpath = os.path.join(ROOT, "tests", "golden", "proof_2p%d_seed20260924.json" % log_n)
+    if os.path.exists(gpath):
+        try:
+            golden_match = bool(json.load(open(gpath))["proof_hex"] == ref_proof.hex())
+        except Exception:
+            golden_match = None
+
     # outside every timed region: the proof that was timed is a valid proof -- the product's verifier (GPU linear
     # combinations + the BN254 pairing against X2 = [tau]_2) accepts it and rejects a tampered copy
     verified = None
@@ -410,6 +421,7 @@ def b200_arm(args):
                 "d2h_bytes_per_step": K * 768, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "proof_verified": verified,
+        "proof_matches_oracle_golden": golden_match,
         "roofline": {"bound": "hbm", "kernel": "k_msm_seg_accumulate", "achieved": achieved, "peak": hbm_gbs,
                      "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": 96.0 * points_per_launch,

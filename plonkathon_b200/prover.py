@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import ctypes
 from dataclasses import dataclass
-from typing import Optional
 
 import numpy as np
 

@@ -10,7 +10,7 @@ from typing import Optional
 from . import _lib
 from .curve import G2, Scalar, _pt_bytes, _pt_from, g2_mul
 from .field import CURVE_ORDER, FIELD_MODULUS, FQ, FQ2
-from .poly import Basis, Polynomial, _log2_exact, scalars_to_bytes
+from .poly import Basis, Polynomial, _log2_exact
 from .verifier import VerificationKey  # noqa: F401  (re-exported: the reference's setup.py imports it too)
 
 SETUP_FILE_G1_STARTPOS = 80  # setup.py:11

@@ -6,6 +6,7 @@ The pure-Python oracle would need hours; this uses oracle/fast.py (same prover c
 C restatement; equivalence checked in tests/test_oracle_fast.py).  One core, 34 minutes, ~7 GB:
 
     python tests/golden/make_proof_2p20.py
+    GOLDEN_SEED=20260924 python tests/golden/make_proof_2p20.py     # bench.py's circuit -> proof_2p20_seed20260924.json
 """
 import hashlib
 import json
@@ -20,7 +21,7 @@ from oracle import plonk_oracle as O  # noqa: E402
 from plonkathon_b200 import synthetic as syn  # noqa: E402
 
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
-LOG_N, SEED, N_PUBLIC = int(os.environ.get("GOLDEN_LOG_N", "20")), 7, 2
+LOG_N, SEED, N_PUBLIC = int(os.environ.get("GOLDEN_LOG_N", "20")), int(os.environ.get("GOLDEN_SEED", "7")), 2
 t0 = time.time()
 
 
@@ -49,6 +50,7 @@ rec = {"log_n": LOG_N, "seed": SEED, "n_public": N_PUBLIC, "tau": hex(TAU), "pub
        "vk": {k: [str(v[0]), str(v[1])] for k, v in vk.items()},
        "generator": "tests/golden/make_proof_2p20.py (oracle/fast.py: plonk_oracle.Prover over the C restatement)",
        "seconds": round(time.time() - t0, 1)}
-out = os.path.join(HERE, "proof_2p20.json" if LOG_N == 20 else "proof_2p%d.json" % LOG_N)
+name = "proof_2p%d" % LOG_N + ("" if SEED == 7 else "_seed%d" % SEED)
+out = os.path.join(HERE, name + ".json")
 json.dump(rec, open(out, "w"), indent=1)
 log("wrote " + out + " sha256 " + rec["sha256"])
