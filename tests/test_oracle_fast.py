@@ -29,14 +29,15 @@ def test_fast_oracle_equals_python_oracle(log_n, seed, n_public):
     assert O.fft is not F.fft  # the patch is undone
 
 
-def test_golden_2p20_record_is_consistent():
-    """the committed golden proof: hash matches the bytes, and the proof verifies under the reference's verification
+@pytest.mark.parametrize("name", ["proof_2p20.json", "proof_2p20_seed20260924.json"])
+def test_golden_2p20_record_is_consistent(name):
+    """the committed golden proofs (the GPU test's circuit, seed 7, and bench.py's, seed 20260924): hash matches the bytes, and the proof verifies under the reference's verification
     equation through the known tau (cheap: a handful of scalar multiplications)"""
     import hashlib
     import json
     import os
     from tests.golden_io import GOLDEN
-    path = os.path.join(GOLDEN, "proof_2p20.json")
+    path = os.path.join(GOLDEN, name)
     if not os.path.exists(path):
         pytest.skip("golden 2^20 proof not generated yet")
     rec = json.load(open(path))
