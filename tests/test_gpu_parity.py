@@ -756,3 +756,25 @@ def test_two_prover_lanes_on_one_gpu(pb):
     with ThreadPoolExecutor(2) as pool:
         got = list(pool.map(worker, range(2)))
     assert got[0] == [alone[0]] * 6 and got[1] == [alone[1]] * 6
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PB200_TEST_2P22") != "1",
+                    reason="opt-in (PB200_TEST_2P22=1): BASELINE.json's largest configuration, ~1 minute and 25 GB of HBM")
+def test_prove_2p22_gates_against_golden(pb):
+    """2^22 gates (4n = 2^24: the three-pass NTT): byte for byte against tests/golden/proof_2p22.json (oracle prover
+    over the C restatement, ~2.5 CPU-hours) when that fixture has been generated, and accepted by the verifier"""
+    import json
+    import os
+    from plonkathon_b200 import synthetic as syn
+    from tests.golden_io import GOLDEN
+    log_n = 22
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=7, n_public=2)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    raw = pb.Prover.from_arrays(setup, n, pk).prove_arrays(A, B, C, public)
+    path = os.path.join(GOLDEN, "proof_2p22.json")
+    if os.path.exists(path):
+        assert raw.hex() == json.load(open(path))["proof_hex"]
+    vk = setup.verification_key_arrays(n, pk)
+    assert vk.verify_proof(n, pb.Proof.from_bytes(raw), [int(x) for x in public])
