@@ -29,7 +29,7 @@ def test_fast_oracle_equals_python_oracle(log_n, seed, n_public):
     assert O.fft is not F.fft  # the patch is undone
 
 
-@pytest.mark.parametrize("name", ["proof_2p20.json", "proof_2p20_seed20260924.json"])
+@pytest.mark.parametrize("name", ["proof_2p20.json", "proof_2p20_seed20260924.json", "proof_2p22.json"])
 def test_golden_2p20_record_is_consistent(name):
     """the committed golden proofs (the GPU test's circuit, seed 7, and bench.py's, seed 20260924): hash matches the bytes, and the proof verifies under the reference's verification
     equation through the known tau (cheap: a handful of scalar multiplications)"""
@@ -43,6 +43,7 @@ def test_golden_2p20_record_is_consistent(name):
     rec = json.load(open(path))
     raw = bytes.fromhex(rec["proof_hex"])
     assert len(raw) == 768 and hashlib.sha256(raw).hexdigest() == rec["sha256"]
-    assert rec["log_n"] == 20 and int(rec["tau"], 16) == TAU
+    log_n = rec["log_n"]
+    assert log_n == int(name.split("_")[1][2:].split(".")[0]) and int(rec["tau"], 16) == TAU
     vk = {k: tuple(int(x) for x in v) for k, v in rec["vk"].items()}
-    assert O.verify_proof_trapdoor(1 << 20, vk, O.proof_from_bytes(raw), [int(x) for x in rec["public"]], TAU)
+    assert O.verify_proof_trapdoor(1 << log_n, vk, O.proof_from_bytes(raw), [int(x) for x in rec["public"]], TAU)
