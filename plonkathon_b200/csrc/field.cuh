@@ -74,6 +74,7 @@ struct FrParams {  // r = 218882428718392752222464057452572750885483644004160343
   static PB_HD constexpr uint32_t p(int i) { return PB_LIMB_SWITCH(i, 0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u); }
   static PB_HD constexpr uint32_t r1(int i) { return PB_LIMB_SWITCH(i, 0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u); }
   static PB_HD constexpr uint32_t r2(int i) { return PB_LIMB_SWITCH(i, 0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u); }
+  static PB_HD constexpr uint32_t r3(int i) { return PB_LIMB_SWITCH(i, 0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu); }
 };
 
 struct FqParams {  // q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
@@ -81,6 +82,7 @@ struct FqParams {  // q = 218882428718392752222464057452572750886963111572978236
   static PB_HD constexpr uint32_t p(int i) { return PB_LIMB_SWITCH(i, 0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u); }
   static PB_HD constexpr uint32_t r1(int i) { return PB_LIMB_SWITCH(i, 0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u); }
   static PB_HD constexpr uint32_t r2(int i) { return PB_LIMB_SWITCH(i, 0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u); }
+  static PB_HD constexpr uint32_t r3(int i) { return PB_LIMB_SWITCH(i, 0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u); }
 };
 
 // --------------------------------------------------------------------------------------------
@@ -93,6 +95,7 @@ struct alignas(16) Fp {
   static PB_HD Fp zero() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
   static PB_HD Fp one() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::r1(i); return r; }   // R mod p
   static PB_HD Fp r2() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::r2(i); return r; }
+  static PB_HD Fp r3() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::r3(i); return r; }            // R^3 mod p
   static PB_HD Fp modulus() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = P::p(i); return r; }
 
   PB_HD bool is_zero() const { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= v[i]; return o == 0; }

@@ -5,8 +5,8 @@
 #include "curve.cuh"
 #include "fieldd.cuh"
 #include "msm_digits.cuh"
-#include "msm_affine.cuh"
 #include "modinv.cuh"
+#include "msm_bucket.cuh"
 #include <vector>
 #include <cstring>
 using namespace pb200;
@@ -48,10 +48,13 @@ int hs_msm_digits(const uint32_t* scalar, uint32_t c, int32_t* digits, uint32_t*
   g.c = c;
   g.W = (256 + c - 1) / c;
   g.half = 1u << (c - 1);
-  g.bucket_stride = g.half;
+  g.fixed_base = 0;
   g.point_stride = 0;
-  g.nb = g.half * g.W;
   g.batch = 1;
+  g.lo = 0;
+  g.nloc = g.half;
+  g.sets = g.W;
+  g.nb = g.half * g.W;
   Fr s = ld<Fr>(scalar);
   DigitWalk dw(&s, 0, 0);
   for (uint32_t w = 0; w < g.W; w++) {
@@ -115,61 +118,141 @@ int hs_curve_op(int op, const uint32_t* acc_in, const uint32_t* other, int other
   return 0;
 }
 
-// Bucket accumulation by rounds of batched affine additions (msm_affine.cuh), every thread body run in a loop.
-// table: n_pts canonical affine points (16 words each); sorted: entries (index | sign << 31) grouped by bucket;
-// offsets: nb + 1.  out: nb canonical affine points + out_inf flags.  Returns the number of rounds, -1 on bad input.
-int hs_msm_affine_rounds(const uint32_t* table, uint32_t n_pts, const uint32_t* sorted, const uint32_t* offsets,
-                         uint32_t nb, uint32_t B, uint32_t F, uint32_t* out, uint8_t* out_inf) {
-  if (B == 0 || F == 0 || F > 64) return -1;
-  std::vector<G1Affine> tab(n_pts);
-  for (uint32_t i = 0; i < n_pts; i++) {
-    tab[i].x = fp_to_mont(ld<Fq>(table + 16 * i));
-    tab[i].y = fp_to_mont(ld<Fq>(table + 16 * i + 8));
+// The whole bucket pipeline of msm.cu on the CPU, every thread body run in a loop: signed-digit slicing, histogram,
+// padded scan, counting-sort scatter, rounds of batched affine additions (msm_bucket.cuh), recursive bucket reduction,
+// bucket-range offset and window Horner.  points: n canonical affine points (16 words each); scalars: batch * n
+// canonical scalars; fixed_base != 0 builds the window table 2^(c w) P_i first (batch <= 4 scalar vectors share it).
+// [lo, hi): the bucket magnitudes this "rank" owns.  out: one canonical affine point (+ identity flag) per scalar
+// vector: the rank's partial sum.  Returns the number of accumulation rounds that did work, -1 on bad input.
+int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars, uint32_t batch, uint32_t c,
+                    int fixed_base, uint32_t lo, uint32_t hi, uint32_t B, uint32_t g0, uint32_t* out, uint8_t* out_inf) {
+  if (!n || !batch || batch > 4 || (!fixed_base && batch != 1) || c < 1 || c > 16 || B < 1 || B > PB_AFF_BMAX) return -1;
+  if (g0 < 2 || (g0 & (g0 - 1))) return -1;
+  MsmGeom g;
+  g.c = c;
+  g.W = (256 + c - 1) / c;
+  g.half = 1u << (c - 1);
+  g.fixed_base = fixed_base ? 1 : 0;
+  g.point_stride = fixed_base ? n : 0;
+  g.batch = batch;
+  if (hi > g.half) hi = g.half;
+  if (lo >= hi) return -1;
+  g.lo = lo;
+  g.nloc = hi - lo;
+  g.sets = fixed_base ? batch : g.W;
+  g.nb = g.sets * g.nloc;
+  // point table
+  std::vector<G1Affine> tab(fixed_base ? (size_t)g.W * n : n);
+  for (uint32_t i = 0; i < n; i++) {
+    tab[i].x = fp_to_mont(ld<Fq>(points + 16 * i));
+    tab[i].y = fp_to_mont(ld<Fq>(points + 16 * i + 8));
   }
-  std::vector<uint32_t> off_in(offsets, offsets + nb + 1), off_out(nb + 1);
-  std::vector<G1Affine> cur, nxt;
-  int rounds = 0;
-  bool first = true;
-  for (;;) {
-    uint32_t maxc = 0;
-    for (uint32_t b = 0; b < nb; b++) maxc = std::max(maxc, off_in[b + 1] - off_in[b]);
-    AffineRound a;
-    a.table = tab.data();
-    a.sorted = first ? sorted : nullptr;
-    a.in = first ? nullptr : cur.data();
-    a.off_in = off_in.data();
-    a.nb = nb;
-    a.B = B;
-    if (maxc <= 1) {
-      for (uint32_t b = 0; b < nb; b++) {
-        G1XYZZ r = affine_round_bucket(a, b);
-        G1Affine p;
-        bool inf = g1_to_affine(r, p);
-        out_inf[b] = inf ? 1 : 0;
-        Fq x = fp_from_mont(p.x), y = fp_from_mont(p.y);
-        st(out + 16 * b, x);
-        st(out + 16 * b + 8, y);
+  if (fixed_base)
+    for (uint32_t w = 1; w < g.W; w++)
+      for (uint32_t i = 0; i < n; i++) {
+        G1XYZZ a;
+        g1_double_affine(a, tab[(size_t)(w - 1) * n + i]);
+        for (uint32_t k = 1; k < c; k++) g1_double(a);
+        g1_to_affine(a, tab[(size_t)w * n + i]);
       }
-      return rounds;
+  std::vector<Fr> sc((size_t)batch * n);
+  for (size_t i = 0; i < sc.size(); i++) sc[i] = ld<Fr>(scalars + 8 * i);
+  // histogram, padded scan, scatter
+  std::vector<uint32_t> counts(g.nb + 1, 0), off(g.nb + 1, 0), cursors(g.nb, 0);
+  for (uint32_t k = 0; k < batch; k++)
+    for (uint32_t i = 0; i < n; i++) {
+      DigitWalk dw(sc.data() + (size_t)k * n, i, 0);
+      for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t neg, d = dw.next(w, g, neg);
+        if (!d) continue;
+        uint32_t key = msm_bucket_key(g, k, w, d);
+        if (key != 0xffffffffu) counts[key]++;
+      }
     }
-    off_out[0] = 0;
-    for (uint32_t b = 0; b < nb; b++) off_out[b + 1] = off_out[b] + ((off_in[b + 1] - off_in[b] + 1) >> 1);
-    const uint32_t S = off_out[nb], T = affine_round_threads(S, B);
-    nxt.assign(S, G1Affine());
-    std::vector<Fq> prefix(S), prod(T + 40);  // a spare warp and a bit: those threads must do nothing
-    std::vector<uint32_t> desc(S);
-    a.off_out = off_out.data();
-    a.out = nxt.data();
-    a.prefix = prefix.data();
-    a.desc = desc.data();
-    a.thread_prod = prod.data();
-    for (uint32_t t = 0; t < T + 40; t++) affine_round_forward(a, t);
-    for (uint32_t u = 0; u < affine_invert_threads(T, F) + 2; u++) affine_round_invert(prod.data(), T, F, u);
-    for (uint32_t t = T + 40; t-- > 0;) affine_round_backward(a, t);
-    cur.swap(nxt);
-    off_in = off_out;
-    first = false;
-    rounds++;
+  uint32_t maxc = 0;
+  for (uint32_t b = 0; b < g.nb; b++) { off[b + 1] = off[b] + ((counts[b] + 1) & ~1u); maxc = std::max(maxc, counts[b]); }
+  counts[g.nb] = maxc;
+  std::vector<uint32_t> sorted(off[g.nb] + 2, PB_MSM_PAD);
+  for (uint32_t k = 0; k < batch; k++)
+    for (uint32_t i = 0; i < n; i++) {
+      DigitWalk dw(sc.data() + (size_t)k * n, i, 0);
+      for (uint32_t w = 0; w < g.W; w++) {
+        uint32_t neg, d = dw.next(w, g, neg);
+        if (!d) continue;
+        uint32_t key = msm_bucket_key(g, k, w, d);
+        if (key == 0xffffffffu) continue;
+        sorted[off[key] + cursors[key]++] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
+      }
+    }
+  // accumulation rounds
+  const uint64_t positions = (uint64_t)n * g.W * batch + g.nb, s_bound = positions / 2;
+  std::vector<G1Affine> pts(s_bound + 1);
+  AffAcc a;
+  a.table = tab.data();
+  a.sorted = sorted.data();
+  a.pts = pts.data();
+  a.off = off.data();
+  a.cnt = counts.data();
+  a.max_cnt = counts.data() + g.nb;
+  a.nbl = g.nb;
+  a.B = B;
+  Fq pref[PB_AFF_BMAX];
+  uint32_t desc[PB_AFF_BMAX];
+  int rounds = 0;
+  for (uint32_t r = 0; r < 32; r++) {
+    a.r = r;
+    if (r > 0 && maxc > (1u << r)) rounds = r + 1;
+    if (r == 0) rounds = 1;
+    const uint64_t T = aff_round_threads(s_bound, B, r) + 40;  // spare threads must do nothing
+    // descending thread order: a right-hand slot read late must still be intact (it is never written in its round)
+    for (uint64_t t = T; t-- > 0;) {
+      if (r == 0) aff_round0_thread(a, t, pref, desc);
+      else aff_round_thread(a, t, pref, desc);
+    }
   }
+  // reduction
+  ReduceArgs ra;
+  ra.pts = pts.data(); ra.off = off.data(); ra.cnt = counts.data(); ra.xb = nullptr; ra.in = nullptr;
+  ra.sets = g.sets; ra.m = g.nloc; ra.g = g0; ra.log_G = 0;
+  std::vector<SR> cur((size_t)g.sets * reduce_groups(ra.m, ra.g)), nxt;
+  ra.out = cur.data();
+  for (uint64_t t = 0; t < cur.size() + 3; t++) reduce_level0_thread(ra, t);
+  uint32_t m = reduce_groups(ra.m, ra.g), log_G = 0;
+  while ((1u << log_G) < g0) log_G++;
+  ra.pts = nullptr;
+  while (m > 1) {
+    nxt.assign((size_t)g.sets * reduce_groups(m, 4), SR());
+    ra.in = cur.data(); ra.out = nxt.data(); ra.m = m; ra.g = 4; ra.log_G = log_G;  // g = 4: more levels per test
+    for (uint64_t t = 0; t < nxt.size() + 3; t++) reduce_level_thread(ra, t);
+    m = reduce_groups(m, 4);
+    log_G += 2;
+    cur.swap(nxt);
+  }
+  std::vector<G1XYZZ> ws(g.sets);
+  for (uint32_t s = 0; s < g.sets; s++) {
+    ws[s] = cur[s].R;
+    G1XYZZ ml = G1XYZZ::identity();
+    for (int i = 31; i >= 0; i--) { g1_double(ml); if ((g.lo >> i) & 1) g1_add(ml, cur[s].S); }
+    g1_add(ws[s], ml);
+  }
+  auto emit = [&](const G1XYZZ& r, uint32_t k) {
+    G1Affine p;
+    bool inf = g1_to_affine(r, p);
+    out_inf[k] = inf ? 1 : 0;
+    Fq x = fp_from_mont(p.x), y = fp_from_mont(p.y);
+    st(out + 16 * k, x);
+    st(out + 16 * k + 8, y);
+  };
+  if (fixed_base) {
+    for (uint32_t k = 0; k < batch; k++) emit(ws[k], k);
+  } else {
+    G1XYZZ r = G1XYZZ::identity();
+    for (int w = (int)g.W - 1; w >= 0; w--) {
+      if (w != (int)g.W - 1) for (uint32_t k = 0; k < c; k++) g1_double(r);
+      g1_add(r, ws[w]);
+    }
+    emit(r, 0);
+  }
+  return rounds;
 }
 }

@@ -1,12 +1,11 @@
-// GROUNDWORK -- not used by the shipped kernels yet: modular inversion by the
-// Bernstein-Yang "safegcd" division steps in batches of 30 on signed 30-bit limbs, for the per-round inversion of the
-// batched-affine bucket accumulation (msm_affine.cuh), where the Fermat chain of fp_inv (380 dependent Montgomery
-// products, ~70 k instructions) is the latency that every round waits for (profiles/r01_msm_affine.md).
-// One batch = 30 division steps on the low words (branch-free; ~40 SASS instructions per step on sm_100a) that produce
-// a 2x2 transition matrix with entries below 2^30 in magnitude, which is then applied to the full-width (f, g) exactly
-// and to (d, e) modulo p: ~1.5 k instructions per batch, at most 25 batches for a 256-bit modulus (741 steps bound),
-// 18 for almost every BN254 input (17-19 over 20 000 random ones): ~28 k instructions per inversion against ~72 k,
-// 66 registers, and no chain of dependent 256-bit multiplications.  Device timing is still to be measured.
+// Modular inversion by the Bernstein-Yang "safegcd" division steps in batches of 30 on signed 30-bit limbs: the
+// per-thread inversion of the batched-affine bucket accumulation (msm_bucket.cuh), where a Fermat chain (fp_inv:
+// 380 dependent Montgomery products) would cost more than the 6 products per addition it amortises.
+// One batch = 30 "half-delta" division steps on the low words (branch-free, ~17 ALU instructions per step) that
+// produce a 2x2 transition matrix with entries below 2^30 in magnitude, which is then applied to the full-width
+// (f, g) exactly and to (d, e) modulo p.  At most 20 batches for a 256-bit modulus (590-step bound); the loop leaves
+// early once g == 0 (uniform enough across a warp: 16-18 batches for almost every BN254 input).  No chain of
+// dependent 256-bit multiplications, no table, same instruction stream on every lane.
 // Host/device code like field.cuh: unit-tested on the CPU against Python's pow(x, -1, p) (tests/test_host_arith.py).
 #pragma once
 #include "field.cuh"
@@ -70,34 +69,34 @@ struct Trans30 {
   int32_t u, v, q, r;  // (f, g) <- (u f + v g, q f + r g) / 2^30
 };
 
-// 30 division steps on the low words.  eta = -delta.  One step:
-//   g odd and eta < 0 : (eta, f, g) <- (-eta, g, -f), then as below
-//   g odd             : g <- g + f
-//   always            : g <- g / 2, eta <- eta - 1
-PB_HD int32_t divsteps30(int32_t eta, uint32_t f0, uint32_t g0, Trans30& t) {
+// 30 division steps on the low words ("half-delta" variant: zeta = -(delta + 1/2), start zeta = -1; 590 steps
+// suffice for any 256-bit modulus, i.e. 20 batches).  Branch-free, ~17 ALU instructions per step:
+//   g odd and zeta < 0 : (f, g) <- (g, (g - f) / 2), zeta <- -zeta - 2
+//   g odd              : g <- (g + f) / 2,           zeta <- zeta - 1
+//   g even             : g <- g / 2,                 zeta <- zeta - 1
+// The transition matrix t accumulates the same operations scaled by 2^30 (entries below 2^30 in magnitude).
+PB_HD int32_t divsteps30(int32_t zeta, uint32_t f0, uint32_t g0, Trans30& t) {
   uint32_t u = 1, v = 0, q = 0, r = 1;  // two's complement; read back as int32
   uint32_t f = f0, g = g0;
+#pragma unroll 6
   for (int i = 0; i < 30; i++) {
-    const uint32_t odd = 0u - (g & 1u);
-    const uint32_t swap = odd & (uint32_t)(eta >> 31);
-    eta = (int32_t)(((uint32_t)eta ^ swap) - swap);  // negate when swapping
-    const uint32_t tf = f, tu = u, tv = v;
-    f = (f & ~swap) | (g & swap);
-    g = (g & ~swap) | ((0u - tf) & swap);
-    u = (u & ~swap) | (q & swap);
-    q = (q & ~swap) | ((0u - tu) & swap);
-    v = (v & ~swap) | (r & swap);
-    r = (r & ~swap) | ((0u - tv) & swap);
-    g += f & odd;
-    q += u & odd;
-    r += v & odd;
+    uint32_t m1 = (uint32_t)(zeta >> 31);  // all ones when zeta < 0
+    const uint32_t m2 = 0u - (g & 1u);     // all ones when g is odd
+    const uint32_t x = (f ^ m1) - m1, y = (u ^ m1) - m1, z = (v ^ m1) - m1;  // +-f, +-u, +-v
+    g += x & m2;
+    q += y & m2;
+    r += z & m2;
+    m1 &= m2;
+    zeta = (int32_t)(((uint32_t)zeta ^ m1) - 1u);
+    f += g & m1;
+    u += q & m1;
+    v += r & m1;
     g >>= 1;  // only the low 30 - i bits of f and g are meaningful, the lost top bit is not one of them
     u <<= 1;
     v <<= 1;
-    eta -= 1;
   }
   t.u = (int32_t)u; t.v = (int32_t)v; t.q = (int32_t)q; t.r = (int32_t)r;
-  return eta;
+  return zeta;
 }
 
 // (f, g) <- t (f, g) / 2^30, exact
@@ -171,7 +170,7 @@ PB_HD Fp<P> fp_inv_plain_gcd(const Fp<P>& x) {
   }
   e.v[0] = 1;
   int32_t eta = -1;
-  for (int batch = 0; batch < 25; batch++) {  // 25 * 30 >= 741 division steps: enough for any 256-bit input
+  for (int batch = 0; batch < 20; batch++) {  // 20 * 30 >= 590 half-delta division steps: enough for any 256-bit input
     int32_t gz = 0;
 #pragma unroll
     for (int i = 0; i < 9; i++) gz |= g.v[i];
@@ -202,8 +201,7 @@ PB_HD Fp<P> fp_inv_plain_gcd(const Fp<P>& x) {
 // Montgomery-form inverse with the same contract as fp_inv: a R -> a^-1 R, inv(0) == 0
 template <class P>
 PB_HD Fp<P> fp_inv_gcd(const Fp<P>& a) {
-  const Fp<P> r3 = fp_mul(Fp<P>::r2(), Fp<P>::r2());  // R^3 mod p
-  return fp_mul(fp_inv_plain_gcd(a), r3);             // (a R)^-1 R^3 R^-1 = a^-1 R
+  return fp_mul(fp_inv_plain_gcd(a), Fp<P>::r3());  // (a R)^-1 R^3 R^-1 = a^-1 R
 }
 
 }  // namespace pb200

@@ -7,20 +7,24 @@
 //      with a global histogram of bucket loads                                  (k_msm_histogram)
 //   2. exclusive scan of the histogram                                           (k_scan_*)
 //   3. counting-sort scatter of (point index, sign) by bucket                    (k_msm_scatter)
-//   4. load-balanced bucket accumulation over fixed segments of the sorted entries: XYZZ accumulator +=
-//      affine point (8M+2S, no inversion), SIMT-uniform loop                     (k_msm_seg_accumulate)
-//      + stitching of buckets that cross a segment boundary                      (k_msm_stitch[_heavy])
-//   5. bucket reduction sum_b (b+1) * B_b by running sums over bucket groups     (k_bucket_groups)
-//      followed by a tree sum of the group results                               (k_sum_points)
-//   6. the few remaining group operations (window Horner, one inversion to affine) on the host,
-//      which has to read the point anyway to feed the Fiat-Shamir transcript.
+//   4. bucket accumulation by rounds of pairwise batched-AFFINE additions, one safegcd inversion per thread
+//      and round: 6 field products per addition (msm_bucket.cuh)               (k_aff_round0 / k_aff_round / k_aff_tail)
+//      [A/B alternative, PB200_MSM_ACC=xyzz: XYZZ accumulators over fixed segments of the sorted entries,
+//       10 products per addition                                      (k_msm_seg_accumulate, k_msm_stitch[_heavy])]
+//   5. bucket reduction sum_b (b+1) * B_b by recursive grouped running sums, one thread per group at every
+//      level                                                                     (k_reduce_level0 / k_reduce_level)
+//   6. the few remaining group operations (bucket-range offset, window Horner, one inversion to affine) on the
+//      host, which has to read the point anyway to feed the Fiat-Shamir transcript.
+// Multi-GPU: a rank may own a BUCKET RANGE [bucket_lo, bucket_hi) of every bucket set -- it walks all digits but
+// sorts, accumulates and reduces only its own buckets, so the whole MSM (not just the accumulation) divides by the
+// number of ranks; or a POINT RANGE (a sub-vector of the points).  Either way it returns XYZZ partial sums.
 // Two modes: "generic" (arbitrary points: W windows x 2^(c-1) buckets) and "fixed-base" (SRS with the
 // window multiples 2^(c*w) * P_i precomputed in HBM: one shared set of 2^(c-1) buckets, no Horner).
 #include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
-#include "msm_affine.cuh"
+#include "msm_bucket.cuh"
 #include "msm_digits.cuh"
 
 namespace pb200 {
@@ -37,7 +41,7 @@ __device__ __forceinline__ G1Affine ld_affine(const G1Affine* p) {
   return r;
 }
 
-// counts[bucket]++ for every non-zero digit
+// counts[bucket]++ for every non-zero digit whose bucket this launch owns
 __global__ void k_msm_histogram(ScalarBatch sb, uint64_t n, int from_mont, MsmGeom g, uint32_t* counts) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -45,12 +49,16 @@ __global__ void k_msm_histogram(ScalarBatch sb, uint64_t n, int from_mont, MsmGe
   DigitWalk dw(sb.p[k], i, from_mont);
   for (uint32_t w = 0; w < g.W; w++) {
     uint32_t neg, d = dw.next(w, g, neg);
-    if (d) atomicAdd(&counts[k * g.half + w * g.bucket_stride + (d - 1)], 1u);
+    if (!d) continue;
+    const uint32_t key = msm_bucket_key(g, k, w, d);
+    if (key != 0xffffffffu) atomicAdd(&counts[key], 1u);
   }
 }
 
 // ---- exclusive scan of the bucket histogram (3 small kernels) ---------------------------------
-// offsets[0..nb] from counts[0..nb-1]; counts are zeroed on the way out (reused as scatter cursors)
+// offsets[0..nb] from counts[0..nb-1]; counts are zeroed on the way out (reused as scatter cursors, which the
+// scatter leaves equal to the counts again).  pad != 0 rounds every count up to even, so all offsets are even
+// (the slot layout of msm_bucket.cuh).
 #define PB_SCAN_TILE 2048  // entries per block (256 threads x 8)
 
 __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* sh, uint32_t* total) {
@@ -78,14 +86,24 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
   return base + x - v;
 }
 
-__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* counts, uint32_t nb, uint32_t* tile_sums) {
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* counts, uint32_t nb, uint32_t pad,
+                                                        uint32_t* tile_sums, uint32_t* max_out) {
   __shared__ uint32_t sh[8];
   uint32_t base = blockIdx.x * PB_SCAN_TILE + threadIdx.x * 8;
-  uint32_t s = 0;
-  for (int k = 0; k < 8; k++) if (base + k < nb) s += counts[base + k];
+  uint32_t s = 0, m = 0;
+  for (int k = 0; k < 8; k++)
+    if (base + k < nb) {
+      uint32_t c = counts[base + k];
+      m = max(m, c);
+      s += (c + pad) & ~pad;
+    }
   uint32_t total;
   block_exclusive_scan_256(s, sh, &total);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+  if (max_out) {  // largest bucket of the launch (decides how many accumulation rounds do work)
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_out, m);
+  }
 }
 
 // single block: exclusive scan of up to 256*32 tile sums in place; writes the grand total to *total_out
@@ -105,13 +123,13 @@ __global__ void __launch_bounds__(256) k_scan_tiles(uint32_t* tile_sums, uint32_
   if (threadIdx.x == 0) *total_out = total;
 }
 
-__global__ void __launch_bounds__(256) k_scan_apply(uint32_t* counts, uint32_t nb, const uint32_t* tile_sums,
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t* counts, uint32_t nb, uint32_t pad, const uint32_t* tile_sums,
                                                     uint32_t* offsets) {
   __shared__ uint32_t sh[8];
   uint32_t base = blockIdx.x * PB_SCAN_TILE + threadIdx.x * 8;
   uint32_t c[8];
   uint32_t s = 0;
-  for (int k = 0; k < 8; k++) { c[k] = base + k < nb ? counts[base + k] : 0; s += c[k]; }
+  for (int k = 0; k < 8; k++) { c[k] = base + k < nb ? (counts[base + k] + pad) & ~pad : 0; s += c[k]; }
   uint32_t total;
   uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan_256(s, sh, &total);
   for (int k = 0; k < 8; k++) {
@@ -129,22 +147,46 @@ __global__ void k_msm_scatter(ScalarBatch sb, uint64_t n, int from_mont, MsmGeom
   DigitWalk dw(sb.p[k], i, from_mont);
   for (uint32_t w = 0; w < g.W; w++) {
     uint32_t neg, d = dw.next(w, g, neg);
-    if (d) {
-      uint32_t key = k * g.half + w * g.bucket_stride + (d - 1);
-      uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
-      sorted[pos] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
-    }
+    if (!d) continue;
+    const uint32_t key = msm_bucket_key(g, k, w, d);
+    if (key == 0xffffffffu) continue;
+    uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
+    sorted[pos] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
   }
 }
 
-// ---- load-balanced bucket accumulation ------------------------------------------------------
-// The sorted entry array is cut into fixed segments of L entries, one thread each, so every thread does
-// the same number of mixed additions no matter how skewed the bucket loads are (real witnesses are full
-// of zeros / ones / small constants, and the top window of a 254-bit scalar is always lopsided).
-// A bucket that lies inside one segment is written directly.  A bucket that crosses a segment boundary
-// leaves partial sums in two slots per segment (slot 2t: the segment's first run, slot 2t+1: its last
-// run); the segment in which the bucket starts "owns" it and stitches the partials together afterwards:
-// by itself when few segments are involved, through a block-wide tree for heavy buckets.
+// ---- batched-affine bucket accumulation (msm_bucket.cuh holds the thread bodies) -----------------------------
+__global__ void __launch_bounds__(128, 4) k_aff_round0(AffAcc a) {
+  Fq pref[PB_AFF_BMAX];
+  uint32_t desc[PB_AFF_BMAX];
+  aff_round0_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, pref, desc);
+}
+__global__ void __launch_bounds__(128, 4) k_aff_round(AffAcc a) {
+  Fq pref[PB_AFF_BMAX];
+  uint32_t desc[PB_AFF_BMAX];
+  aff_round_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, pref, desc);
+}
+// rounds PB_AFF_GRID_ROUNDS.. of buckets with more than 2^PB_AFF_GRID_ROUNDS entries (skewed scalars only): one
+// block walks the remaining rounds with a barrier in between; returns at once in the common case
+__global__ void __launch_bounds__(256) k_aff_tail(AffAcc a, uint64_t s_bound) {
+  Fq pref[PB_AFF_BMAX];
+  uint32_t desc[PB_AFF_BMAX];
+  const uint32_t maxc = *a.max_cnt;
+  for (uint32_t r = PB_AFF_GRID_ROUNDS; r < 32 && maxc > (1u << r); r++) {
+    a.r = r;
+    const uint64_t T = aff_round_threads(s_bound, a.B, r);
+    for (uint64_t t = threadIdx.x; t < T; t += blockDim.x) aff_round_thread(a, t, pref, desc);
+    __syncthreads();
+  }
+}
+
+// ---- A/B alternative: load-balanced XYZZ accumulation --------------------------------------------------------
+// The sorted entry array (unpadded offsets) is cut into fixed segments of L entries, one thread each, so every
+// thread does the same number of mixed additions no matter how skewed the bucket loads are.  A bucket that lies
+// inside one segment is written directly.  A bucket that crosses a segment boundary leaves partial sums in two
+// slots per segment (slot 2t: the segment's first run, slot 2t+1: its last run); the segment in which the bucket
+// starts "owns" it and stitches the partials together afterwards: by itself when few segments are involved,
+// through a block-wide tree for heavy buckets.
 #define PB_MSM_EMPTY 0xffffffffu
 
 __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* a, uint32_t n, uint32_t key) {
@@ -196,34 +238,6 @@ __global__ void __launch_bounds__(128) k_msm_seg_accumulate(const G1Affine* poin
     if (v >> 31) p.y = fp_neg(p.y);
     g1_add_mixed_uniform(acc, p);
   }
-}
-
-
-// ---- batched-affine bucket accumulation (msm_affine.cuh holds the thread bodies) ---------------------------------
-__global__ void __launch_bounds__(128) k_aff_forward(AffineRound a) {
-  affine_round_forward(a, blockIdx.x * blockDim.x + threadIdx.x);
-}
-__global__ void __launch_bounds__(128) k_aff_invert(Fq* prod, const uint32_t* slots_total, uint32_t B, uint32_t F) {
-  const uint32_t n = affine_round_threads(*slots_total, B);
-  affine_round_invert(prod, n, F, blockIdx.x * blockDim.x + threadIdx.x);
-}
-__global__ void __launch_bounds__(128) k_aff_backward(AffineRound a) {
-  affine_round_backward(a, blockIdx.x * blockDim.x + threadIdx.x);
-}
-// counts[b] = ceil(size of bucket b / 2): the next round's bucket sizes (scanned into its offsets)
-__global__ void k_aff_half_counts(const uint32_t* off_in, uint32_t nb, uint32_t* counts) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nb) counts[b] = (off_in[b + 1] - off_in[b] + 1) >> 1;
-}
-__global__ void k_aff_buckets(AffineRound a, G1XYZZ* buckets) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.nb) buckets[b] = affine_round_bucket(a, b);
-}
-__global__ void k_max_u32(const uint32_t* v, uint32_t n, uint32_t* out) {
-  uint32_t m = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
-  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 struct HeavyItem { uint32_t bucket, own_slot, t0, t1; };
@@ -282,68 +296,12 @@ __global__ void __launch_bounds__(128) k_msm_stitch_heavy(const G1XYZZ* slots, c
   }
 }
 
-// acc = k * p (k < 2^31), double-and-add from the top bit
-__device__ G1XYZZ g1_mul_small(const G1XYZZ& p, uint32_t k) {
-  G1XYZZ r = G1XYZZ::identity();
-  for (int i = 31; i >= 0; i--) {
-    g1_double(r);
-    if ((k >> i) & 1) g1_add(r, p);
-  }
-  return r;
+// ---- bucket reduction (msm_bucket.cuh) --------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_reduce_level0(ReduceArgs a) {
+  reduce_level0_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-
-// group t covers bucket indices [lo, lo+gsz) of one window; out[t] = sum_{idx} (idx_in_window + 1) * B
-__global__ void __launch_bounds__(128) k_bucket_groups(const G1XYZZ* buckets, uint32_t half, uint32_t gsz,
-                                                       uint32_t n_groups_total, G1XYZZ* out) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_groups_total) return;
-  uint32_t groups_per_window = (half + gsz - 1) / gsz;  // the last group of a window may be shorter
-  uint32_t w = t / groups_per_window, gi = t % groups_per_window;
-  uint32_t lo = gi * gsz;
-  uint32_t len = min(gsz, half - lo);
-  const G1XYZZ* base = buckets + (uint64_t)w * half + lo;
-  // running sums, software-pipelined: acc_(k-1) = acc_k + B_(k-1) does not depend on sum += acc_k, so the two
-  // additions of an iteration are independent and can be interleaved (select-based adds: one instruction stream)
-  G1XYZZ acc = base[len - 1], sum = G1XYZZ::identity();
-  for (int k = (int)len - 1; k >= 0; k--) {
-    G1XYZZ nxt = acc;
-    if (k > 0) {
-      G1XYZZ bk = base[k - 1];
-      g1_add_uniform(nxt, bk);
-    }
-    g1_add_uniform(sum, acc);
-    acc = nxt;
-  }
-  if (lo) {
-    G1XYZZ m = g1_mul_small(acc, lo);
-    g1_add(sum, m);
-  }
-  out[t] = sum;
-}
-
-// out[w * gridDim.x + blockIdx.x] = sum of this block's 128-point slice of in[w * per .. (w+1) * per)
-// (blockIdx.y = w).  Applied twice it sums up to 16384 points per window with 7-deep trees only.
-__global__ void __launch_bounds__(128) k_sum_points(const G1XYZZ* in, uint32_t per, G1XYZZ* out) {
-  __shared__ G1XYZZ sh[128];
-  const G1XYZZ* base = in + (uint64_t)blockIdx.y * per;
-  uint32_t chunk = (per + gridDim.x - 1) / gridDim.x;
-  uint32_t lo = blockIdx.x * chunk, hi = min(lo + chunk, per);
-  G1XYZZ acc = G1XYZZ::identity();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    G1XYZZ v = base[i];
-    g1_add(acc, v);
-  }
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
-    if (threadIdx.x < d) {
-      G1XYZZ a = sh[threadIdx.x], b = sh[threadIdx.x + d];
-      g1_add(a, b);
-      sh[threadIdx.x] = a;
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
+__global__ void __launch_bounds__(128) k_reduce_level(ReduceArgs a) {
+  reduce_level_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // affine points: canonical <-> Montgomery (both coordinates)
@@ -395,7 +353,7 @@ __global__ void __launch_bounds__(128) k_batch_to_affine(const G1XYZZ* in, G1Aff
     pref[k] = run;                      // product of ZZZ[0..k)
     run = fp_mul(run, in[i0 + k].ZZZ);
   }
-  Fq inv = fp_inv(run);
+  Fq inv = fp_inv_gcd(run);
   for (int k = cnt - 1; k >= 0; k--) {
     G1XYZZ a = in[i0 + k];
     Fq A = fp_mul(inv, pref[k]);        // 1 / ZZZ_k
@@ -431,6 +389,16 @@ uint32_t msm_default_window(uint64_t n, bool fixed_base) {
   return (uint32_t)c;
 }
 
+// k * p for a small k (host arithmetic, double-and-add)
+static G1XYZZ host_mul_small(const G1XYZZ& p, uint32_t k) {
+  G1XYZZ r = G1XYZZ::identity();
+  for (int i = 31; i >= 0; i--) {
+    g1_double(r);
+    if ((k >> i) & 1) g1_add(r, p);
+  }
+  return r;
+}
+
 static void host_horner_to_affine(const std::vector<G1XYZZ>& ws, uint32_t c, uint8_t* out_xy, int* is_identity) {
   G1XYZZ r = G1XYZZ::identity();
   for (int w = (int)ws.size() - 1; w >= 0; w--) {
@@ -446,149 +414,123 @@ static void host_horner_to_affine(const std::vector<G1XYZZ>& ws, uint32_t c, uin
   memcpy(out_xy + 32, y.v, 32);
 }
 
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* e = getenv(name);
+  return e ? (uint32_t)atoi(e) : dflt;
+}
+
+// additions per thread of an accumulation round over `items` candidate additions: as many as BMAX while the launch
+// still fills the machine a few times over (a thread's inversion is amortised over its additions)
+static uint32_t pick_B(Context* ctx, uint64_t items) {
+  static const uint32_t forced = env_u32("PB200_MSM_B", 0);
+  if (forced) return std::min<uint32_t>(std::max<uint32_t>(forced, 1), PB_AFF_BMAX);
+  const uint64_t resident = (uint64_t)ctx->sm_count * 512;
+  for (uint32_t B : {64u, 48u, 32u, 24u}) if (items / B >= 3 * resident) return B;
+  return 16;
+}
+
 // points: Montgomery affine (generic: n points; fixed-base: expanded table W*n).
-// batch > 1 (fixed-base only): `batch` scalar vectors against the same points in one pass; the k-th MSM
-// uses bucket set k, which the reduction phase treats exactly like an extra window.
+// batch > 1 (fixed-base only): `batch` scalar vectors against the same points in one pass; the k-th MSM uses bucket
+// set k.  [bucket_lo, bucket_hi): the bucket magnitudes this call owns (0, 2^(c-1) = everything); with a proper
+// sub-range the result is this rank's partial sum.
 void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* const* scalars, uint32_t batch,
-                   bool scalars_mont, uint32_t c, bool fixed_base, uint64_t point_stride, uint8_t* out_xy /*batch*64*/,
-                   int* is_identity /*batch*/, G1XYZZ* raw_out /*optional: batch XYZZ sums instead of affine*/) {
+                   bool scalars_mont, uint32_t c, bool fixed_base, uint64_t point_stride, uint32_t bucket_lo,
+                   uint32_t bucket_hi, uint8_t* out_xy /*batch*64*/, int* is_identity /*batch*/,
+                   G1XYZZ* raw_out /*optional: batch XYZZ sums instead of affine*/) {
   PB_CHECK(n > 0, "empty MSM");
   PB_CHECK(batch >= 1 && batch <= 4 && (fixed_base || batch == 1), "bad MSM batch");
   MsmGeom g;
   g.c = c;
   g.W = windows_for(c);
   g.half = 1u << (c - 1);
-  g.bucket_stride = fixed_base ? 0 : g.half;
+  g.fixed_base = fixed_base ? 1 : 0;
   g.point_stride = fixed_base ? point_stride : 0;
-  g.nb = fixed_base ? g.half * batch : g.half * g.W;
   g.batch = batch;
+  if (bucket_hi > g.half) bucket_hi = g.half;
+  PB_CHECK(bucket_lo < bucket_hi, "empty MSM bucket range");
+  g.lo = bucket_lo;
+  g.nloc = bucket_hi - bucket_lo;
+  g.sets = fixed_base ? batch : g.W;
+  g.nb = g.sets * g.nloc;
   PB_CHECK((fixed_base ? (uint64_t)g.W * point_stride : n) < (1ull << 31), "MSM too large for 31-bit point ids");
-  uint32_t n_windows_out = fixed_base ? batch : g.W;
   ScalarBatch sb;
   for (uint32_t k = 0; k < 4; k++) sb.p[k] = k < batch ? scalars[k] : nullptr;
 
+  static const bool use_xyzz = [] { const char* e = getenv("PB200_MSM_ACC"); return e && !strcmp(e, "xyzz"); }();
+  const uint32_t pad = use_xyzz ? 0 : 1;
   DevBuf& sorted = ctx->scratch[2];
   DevBuf& counts = ctx->scratch[3];
   DevBuf& offsets = ctx->scratch[4];
-  DevBuf& buckets = ctx->scratch[5];
-  DevBuf& groups = ctx->scratch[6];
-  DevBuf& wsums = ctx->scratch[7];
-  DevBuf& seg = ctx->scratch[1];
-  uint32_t seg_len = 32;
-  if (const char* e = getenv("PB200_MSM_SEG")) seg_len = (uint32_t)atoi(e);
-  PB_CHECK(seg_len >= 1 && seg_len <= 4096, "bad PB200_MSM_SEG");
-  uint64_t entries = n * g.W * batch;
-  PB_CHECK(entries < (1ull << 32), "MSM too large (n * windows must fit 32 bits)");
-  sorted.ensure(entries * 4);
-  counts.ensure((size_t)g.nb * 4);
+  DevBuf& lvl_a = ctx->scratch[6];
+  DevBuf& lvl_b = ctx->scratch[7];
+  const uint64_t entries = n * g.W * batch;           // upper bound (every digit non-zero and owned)
+  const uint64_t positions = entries + (pad ? g.nb : 0);  // with the padding to even bucket sizes
+  PB_CHECK(positions < (1ull << 30), "MSM too large (n * windows * batch must stay below 2^30)");
+  sorted.ensure(positions * 4);
+  counts.ensure((size_t)g.nb * 4 + 16);
   offsets.ensure((size_t)(g.nb + 1) * 4);
-  buckets.ensure((size_t)g.nb * sizeof(G1XYZZ));
-  // group size of the bucket reduction: at least 32 buckets per thread, and large enough that all groups of
-  // the launch are resident at once (the kernel holds 256 threads per SM; a 1.3-wave grid costs two waves)
-  uint32_t gsz = g.half >= 32 ? 32 : g.half;
-  {
-    uint64_t resident = (uint64_t)ctx->sm_count * 256;
-    uint32_t fit = (uint32_t)(((uint64_t)g.nb + resident - 1) / resident);
-    if (fit > gsz && fit <= 2 * gsz) {
-      // keep the groups from straddling windows: choose the per-window count first
-      uint32_t per_window = (uint32_t)(resident / n_windows_out);
-      gsz = (g.half + per_window - 1) / per_window;
-    }
-  }
-  uint32_t groups_per_window = (g.half + gsz - 1) / gsz;
-  uint32_t n_groups = groups_per_window * n_windows_out;
-  groups.ensure(((size_t)n_groups + (size_t)n_windows_out * 1024) * sizeof(G1XYZZ));
-  wsums.ensure((size_t)n_windows_out * sizeof(G1XYZZ) + 8192 * 4);
-
-  cudaStream_t st = ctx->stream;
-  PB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)g.nb * 4, st));
-  unsigned blocks = (unsigned)((n + 127) / 128);
-  k_msm_histogram<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
+  uint32_t* max_cnt = counts.as<uint32_t>() + g.nb;
   const uint32_t n_tiles = (g.nb + PB_SCAN_TILE - 1) / PB_SCAN_TILE;
   PB_CHECK(n_tiles <= 8192, "too many buckets for the scan");
-  uint32_t* tile_sums = reinterpret_cast<uint32_t*>(wsums.as<unsigned char>() + (size_t)n_windows_out * sizeof(G1XYZZ));
-  // exclusive scan of `counts` into `off` (nb + 1 entries); leaves counts zeroed
-  auto scan_counts = [&](uint32_t* off) {
-    k_scan_tile_sums<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums);
-    k_scan_tiles<<<1, 256, 0, st>>>(tile_sums, n_tiles, off + g.nb);
-    k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, tile_sums, off);
-  };
-  bool affine = false;
-  if (const char* e = getenv("PB200_MSM_AFFINE")) affine = atoi(e) != 0;
-  if (entries >= (1ull << PB_AFF_INDEX_BITS)) affine = false;  // slot descriptors carry 29-bit element indices
-  uint32_t* max_count = nullptr;
-  if (affine) {
-    ctx->msm_aff[5].ensure((size_t)(g.nb + 1) * 4 + 16);
-    max_count = ctx->msm_aff[5].as<uint32_t>() + (g.nb + 1);
-    PB_CUDA(cudaMemsetAsync(max_count, 0, 4, st));
-    k_max_u32<<<ctx->sm_count * 4, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, max_count);
-    ctx->launches++;
-  }
-  scan_counts(offsets.as<uint32_t>());
+  ctx->msm_aff[1].ensure((size_t)8192 * 4);
+  uint32_t* tile_sums = ctx->msm_aff[1].as<uint32_t>();
+
+  cudaStream_t st = ctx->stream;
+  ctx->time_begin(2);
+  PB_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)g.nb * 4 + 16, st));
+  if (pad) PB_CUDA(cudaMemsetAsync(sorted.p, 0xff, positions * 4, st));
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  k_msm_histogram<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, counts.as<uint32_t>());
+  k_scan_tile_sums<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, pad, tile_sums, max_cnt);
+  k_scan_tiles<<<1, 256, 0, st>>>(tile_sums, n_tiles, offsets.as<uint32_t>() + g.nb);
+  k_scan_apply<<<n_tiles, 256, 0, st>>>(counts.as<uint32_t>(), g.nb, pad, tile_sums, offsets.as<uint32_t>());
   k_msm_scatter<<<dim3(blocks, batch), 128, 0, st>>>(sb, n, scalars_mont ? 1 : 0, g, offsets.as<uint32_t>(),
                                                      counts.as<uint32_t>(), sorted.as<uint32_t>());
-  if (affine) {
-    // rounds of batched affine additions (msm_affine.cuh): bucket sizes halve each round
-    uint32_t h_max = 0;
-    PB_CUDA(cudaMemcpyAsync(&h_max, max_count, 4, cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
-    uint32_t rounds = 0;
-    while ((1ull << rounds) < h_max) rounds++;
-    uint32_t B = 32, F = 16;
-    if (const char* e = getenv("PB200_MSM_AFFINE_B")) B = (uint32_t)atoi(e);
-    if (const char* e = getenv("PB200_MSM_AFFINE_F")) F = (uint32_t)atoi(e);
-    PB_CHECK(B >= 1 && B <= 4096 && F >= 1 && F <= 64, "bad PB200_MSM_AFFINE_B / PB200_MSM_AFFINE_F");
-    // upper bounds of the slot counts (the exact ones live on the device): S' <= (S + #non-empty buckets) / 2
-    auto half_bound = [&](uint64_t s_in) { return (s_in + std::min<uint64_t>(g.nb, s_in) + 1) / 2; };
-    const uint64_t s1_bound = half_bound(entries), s2_bound = half_bound(s1_bound);
-    DevBuf& buf_a = ctx->msm_aff[0];
-    DevBuf& buf_b = ctx->msm_aff[1];
-    DevBuf& prefix = ctx->msm_aff[2];
-    DevBuf& desc = ctx->msm_aff[3];
-    DevBuf& tprod = ctx->msm_aff[4];
-    if (rounds >= 1) {
-      buf_a.ensure(s1_bound * sizeof(G1Affine));
-      prefix.ensure(s1_bound * sizeof(Fq));
-      desc.ensure(s1_bound * 4);
-      tprod.ensure((size_t)affine_round_threads((uint32_t)s1_bound, B) * sizeof(Fq));
-    }
-    if (rounds >= 2) buf_b.ensure(s2_bound * sizeof(G1Affine));
-    uint32_t* off_cur = offsets.as<uint32_t>();
-    uint32_t* off_nxt = ctx->msm_aff[5].as<uint32_t>();
-    AffineRound a;
+  ctx->time_end(2);
+  ctx->launches += 5;
+
+  ReduceArgs ra;
+  ra.pts = nullptr; ra.off = offsets.as<uint32_t>(); ra.cnt = counts.as<uint32_t>(); ra.xb = nullptr;
+  if (!use_xyzz) {
+    // rounds of batched affine additions, in place on the slot array (msm_bucket.cuh)
+    const uint64_t s_bound = positions / 2;
+    DevBuf& pts = ctx->msm_aff[0];
+    pts.ensure(s_bound * sizeof(G1Affine));
+    AffAcc a;
     a.table = points;
     a.sorted = sorted.as<uint32_t>();
-    a.in = nullptr;
-    a.nb = g.nb;
-    a.B = B;
-    a.prefix = prefix.as<Fq>();
-    a.desc = desc.as<uint32_t>();
-    a.thread_prod = tprod.as<Fq>();
-    uint64_t bound = entries;
+    a.pts = pts.as<G1Affine>();
+    a.off = offsets.as<uint32_t>();
+    a.cnt = counts.as<uint32_t>();
+    a.max_cnt = max_cnt;
+    a.nbl = g.nb;
+    // no bucket can hold more than n * W entries (fixed-base) / n entries (generic): rounds beyond that never run
+    uint64_t cap = fixed_base ? n * g.W : n;
+    uint32_t max_rounds = 1;
+    while (max_rounds < 32 && (1ull << max_rounds) < cap) max_rounds++;
     ctx->time_begin(0);
-    for (uint32_t r = 0; r < rounds; r++) {
-      k_aff_half_counts<<<(g.nb + 255) / 256, 256, 0, st>>>(off_cur, g.nb, counts.as<uint32_t>());
-      scan_counts(off_nxt);
-      bound = half_bound(bound);
-      const uint32_t threads = affine_round_threads((uint32_t)bound, B);
-      a.off_in = off_cur;
-      a.off_out = off_nxt;
-      a.out = ((r & 1) ? buf_b : buf_a).as<G1Affine>();
-      k_aff_forward<<<(threads + 127) / 128, 128, 0, st>>>(a);
-      k_aff_invert<<<(affine_invert_threads(threads, F) + 127) / 128, 128, 0, st>>>(a.thread_prod, off_nxt + g.nb, B, F);
-      k_aff_backward<<<(threads + 127) / 128, 128, 0, st>>>(a);
-      ctx->launches += 7;
-      a.sorted = nullptr;
-      a.in = a.out;
-      std::swap(off_cur, off_nxt);
+    for (uint32_t r = 0; r < std::min<uint32_t>(max_rounds, PB_AFF_GRID_ROUNDS); r++) {
+      a.r = r;
+      a.B = pick_B(ctx, s_bound >> r);
+      const uint64_t threads = aff_round_threads(s_bound, a.B, r);
+      if (r == 0) k_aff_round0<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
+      else k_aff_round<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
+      ctx->launches++;
     }
-    a.off_in = off_cur;
-    k_aff_buckets<<<(g.nb + 127) / 128, 128, 0, st>>>(a, buckets.as<G1XYZZ>());
+    if (max_rounds > PB_AFF_GRID_ROUNDS) {
+      a.B = 16;
+      k_aff_tail<<<1, 256, 0, st>>>(a, s_bound);
+      ctx->launches++;
+    }
     ctx->time_end(0);
-    ctx->launches -= 2;  // the fixed "+= 10" below counts accumulate + 2 x stitch; this path has k_aff_buckets only
+    ra.pts = pts.as<G1Affine>();
   } else {
-    // balanced accumulation over fixed segments of L sorted entries
-    const uint32_t L = seg_len;
+    // balanced XYZZ accumulation over fixed segments of L sorted entries
+    DevBuf& buckets = ctx->scratch[5];
+    DevBuf& seg = ctx->scratch[1];
+    buckets.ensure((size_t)g.nb * sizeof(G1XYZZ));
+    const uint32_t L = env_u32("PB200_MSM_SEG", 32);
+    PB_CHECK(L >= 1 && L <= 4096, "bad PB200_MSM_SEG");
     const uint32_t n_seg = (uint32_t)((entries + L - 1) / L);
     seg.ensure((size_t)n_seg * 2 * sizeof(G1XYZZ) + (size_t)n_seg * 3 * 4 + (size_t)n_seg * sizeof(HeavyItem) + 16);
     G1XYZZ* slots = seg.as<G1XYZZ>();
@@ -606,29 +548,71 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     k_msm_stitch<<<(n_seg + 127) / 128, 128, 0, st>>>(offsets.as<uint32_t>(), g.nb, L, n_seg, slots, slot_bucket,
                                                      own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, 16);
     k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, buckets.as<G1XYZZ>());
+    ctx->launches += 3;
+    ra.xb = buckets.as<G1XYZZ>();
   }
-  k_bucket_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(buckets.as<G1XYZZ>(), g.half, gsz, n_groups,
-                                                         groups.as<G1XYZZ>());
+
+  // bucket reduction: levels of grouped running sums until one (S, R) pair per set is left
+  static const uint32_t g0_env = env_u32("PB200_MSM_G", 16);
+  uint32_t log_g0 = 4;
+  while ((1u << log_g0) < g0_env && log_g0 < 10) log_g0++;
+  if ((1u << log_g0) > g0_env && log_g0 > 1) log_g0--;
+  ctx->time_begin(3);
+  ra.sets = g.sets;
+  ra.m = g.nloc;
+  ra.g = 1u << log_g0;
+  ra.log_G = 0;
+  ra.in = nullptr;
   {
-    uint32_t per = groups_per_window;                  // group results per window
-    uint32_t mid = per > 128 ? (per + 127) / 128 : 1;  // first-level blocks per window
-    G1XYZZ* level1 = groups.as<G1XYZZ>() + n_groups;
-    if (mid > 1) {
-      k_sum_points<<<dim3(mid, n_windows_out), 128, 0, st>>>(groups.as<G1XYZZ>(), per, level1);
-      k_sum_points<<<dim3(1, n_windows_out), 128, 0, st>>>(level1, mid, wsums.as<G1XYZZ>());
-      ctx->launches++;  // the second tree level
-    } else {
-      k_sum_points<<<dim3(1, n_windows_out), 128, 0, st>>>(groups.as<G1XYZZ>(), per, wsums.as<G1XYZZ>());
+    const uint64_t groups = (uint64_t)g.sets * reduce_groups(ra.m, ra.g);
+    lvl_a.ensure(groups * sizeof(SR));
+    lvl_b.ensure((groups / 16 + g.sets) * sizeof(SR));
+    ra.out = lvl_a.as<SR>();
+    k_reduce_level0<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(ra);
+    ctx->launches++;
+  }
+  uint32_t m = reduce_groups(ra.m, ra.g), log_G = log_g0;
+  SR* cur = lvl_a.as<SR>();
+  SR* nxt = lvl_b.as<SR>();
+  ra.pts = nullptr; ra.xb = nullptr;
+  while (m > 1) {
+    ra.in = cur;
+    ra.out = nxt;
+    ra.m = m;
+    ra.g = 16;
+    ra.log_G = log_G;
+    const uint64_t groups = (uint64_t)g.sets * reduce_groups(m, 16);
+    k_reduce_level<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(ra);
+    ctx->launches++;
+    m = reduce_groups(m, 16);
+    log_G += 4;
+    std::swap(cur, nxt);
+  }
+  ctx->time_end(3);
+  PB_CUDA(cudaGetLastError());
+  std::vector<SR> fin(g.sets);
+  PB_CUDA(cudaMemcpyAsync(fin.data(), cur, g.sets * sizeof(SR), cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  // set result = sum_j (lo + j + 1) B_j = R + lo * S
+  std::vector<G1XYZZ> ws(g.sets);
+  for (uint32_t s = 0; s < g.sets; s++) {
+    ws[s] = fin[s].R;
+    if (g.lo) {
+      G1XYZZ m_lo = host_mul_small(fin[s].S, g.lo);
+      g1_add(ws[s], m_lo);
     }
   }
-  ctx->launches += 10;  // histogram, 3 x scan, scatter, accumulate, stitch, stitch_heavy, bucket_groups, sum_points
-  PB_CUDA(cudaGetLastError());
-  std::vector<G1XYZZ> ws(n_windows_out);
-  PB_CUDA(cudaMemcpyAsync(ws.data(), wsums.p, n_windows_out * sizeof(G1XYZZ), cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaStreamSynchronize(st));
   if (raw_out) {
-    PB_CHECK(fixed_base, "raw MSM output is only available in fixed-base mode");
-    for (uint32_t k = 0; k < batch; k++) raw_out[k] = ws[k];
+    if (fixed_base) {
+      for (uint32_t k = 0; k < batch; k++) raw_out[k] = ws[k];
+    } else {  // window Horner without the final conversion
+      G1XYZZ r = G1XYZZ::identity();
+      for (int w = (int)g.W - 1; w >= 0; w--) {
+        if (w != (int)g.W - 1) for (uint32_t k = 0; k < c; k++) g1_double(r);
+        g1_add(r, ws[w]);
+      }
+      raw_out[0] = r;
+    }
   } else if (fixed_base) {
     for (uint32_t k = 0; k < batch; k++) {
       std::vector<G1XYZZ> one(1, ws[k]);
@@ -641,7 +625,8 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
 
 void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars, bool scalars_mont, uint32_t c,
              bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity) {
-  msm_run_batch(ctx, points, n, &scalars, 1, scalars_mont, c, fixed_base, point_stride, out_xy, is_identity, nullptr);
+  msm_run_batch(ctx, points, n, &scalars, 1, scalars_mont, c, fixed_base, point_stride, 0, 0xffffffffu, out_xy,
+                is_identity, nullptr);
 }
 
 // ---- SRS --------------------------------------------------------------------------------
@@ -793,28 +778,32 @@ void srs_msm_batch(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t 
                    uint8_t* out_xy, int* is_identity) {
   PB_CHECK(m <= srs->n, "Not enough powers in setup");
   if (srs->expanded.p && batch > 1) {
-    msm_run_batch(ctx, srs->expanded.as<G1Affine>(), m, d_scalars, batch, scalars_mont, srs->c, true, srs->n, out_xy,
-                  is_identity, nullptr);
+    msm_run_batch(ctx, srs->expanded.as<G1Affine>(), m, d_scalars, batch, scalars_mont, srs->c, true, srs->n, 0,
+                  0xffffffffu, out_xy, is_identity, nullptr);
   } else {
     for (uint32_t k = 0; k < batch; k++) srs_msm(ctx, srs, d_scalars[k], m, scalars_mont, out_xy + 64 * k, is_identity + k);
   }
 }
 
-// Point-range shard of `batch` commitments: sum over i in [first, first + count) of scalars[k][i] * P_i,
-// returned as XYZZ partial sums (Montgomery) for the caller to exchange and combine (multi-GPU MSM join).
+// Shard of `batch` commitments to m coefficients, returned as XYZZ partial sums (Montgomery) for the caller to
+// exchange and add (multi-GPU MSM join).  Two ways to cut, which compose:
+//   point range  [first, first + count): sum over those SRS powers only (each rank needs only its scalars' slab);
+//   bucket range [bucket_lo, bucket_hi) of the 2^(c-1) signed-digit magnitudes: the rank walks all digits but sorts,
+//                accumulates and reduces only its own buckets, so the bucket reduction divides by the rank count too.
 void srs_msm_batch_partial(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t first,
-                           uint64_t count, bool scalars_mont, G1XYZZ* out) {
+                           uint64_t count, uint32_t bucket_lo, uint32_t bucket_hi, bool scalars_mont, G1XYZZ* out) {
   PB_CHECK(first + count <= srs->n, "Not enough powers in setup");
   PB_CHECK(srs->expanded.p, "sharded commitments need the fixed-base table (precompute)");
   const Fr* sh[4] = {nullptr, nullptr, nullptr, nullptr};
   for (uint32_t k = 0; k < batch; k++) sh[k] = d_scalars[k] + first;
-  if (count == 0) {
+  if (count == 0 || bucket_lo >= bucket_hi) {
     for (uint32_t k = 0; k < batch; k++) out[k] = G1XYZZ::identity();
     return;
   }
-  msm_run_batch(ctx, srs->expanded.as<G1Affine>() + first, count, sh, batch, scalars_mont, srs->c, true, srs->n, nullptr,
-                nullptr, out);
+  msm_run_batch(ctx, srs->expanded.as<G1Affine>() + first, count, sh, batch, scalars_mont, srs->c, true, srs->n,
+                bucket_lo, bucket_hi, nullptr, nullptr, out);
 }
+uint32_t srs_bucket_count(Srs* s) { return s->c ? 1u << (s->c - 1) : 0; }
 
 // sum of XYZZ partials -> canonical affine (host arithmetic; O(count) group operations)
 void g1_combine_partials_host(const G1XYZZ* parts, uint32_t count, uint8_t* out_xy, int* is_identity) {

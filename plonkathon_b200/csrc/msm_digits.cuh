@@ -8,11 +8,20 @@ namespace pb200 {
 struct MsmGeom {
   uint32_t c, W;            // window bits, number of windows
   uint32_t half;            // 2^(c-1) buckets per window
-  uint32_t bucket_stride;   // generic: half ; fixed-base: 0
+  uint32_t fixed_base;      // 1: one bucket set per batched scalar vector, shared by all windows; 0: one per window
   uint64_t point_stride;    // generic: 0 ; fixed-base: n (index of window w's copy of point i = w*n + i)
-  uint32_t nb;              // total buckets
-  uint32_t batch;           // fixed-base only: number of MSMs sharing the points (bucket set k at k * half)
+  uint32_t batch;           // fixed-base only: number of MSMs sharing the points
+  uint32_t lo, nloc;        // this launch owns bucket magnitudes d with lo <= d - 1 < lo + nloc (bucket-range shard)
+  uint32_t sets;            // bucket sets: fixed-base: batch ; generic: W
+  uint32_t nb;              // sets * nloc local buckets
 };
+
+// local bucket of digit magnitude d >= 1 of window w of scalar vector k, or 0xffffffff when another rank owns it
+PB_HD uint32_t msm_bucket_key(const MsmGeom& g, uint32_t k, uint32_t w, uint32_t d) {
+  const uint32_t j = d - 1 - g.lo;  // wraps for d - 1 < lo
+  if (j >= g.nloc) return 0xffffffffu;
+  return (g.fixed_base ? k : w) * g.nloc + j;
+}
 
 struct ScalarBatch { const Fr* p[4]; };
 

@@ -9,7 +9,8 @@ void srs_msm(Context* ctx, Srs* srs, const Fr* d_scalars, uint64_t m, bool scala
 void srs_msm_batch(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t m, bool scalars_mont,
                    uint8_t* out_xy, int* is_identity);
 void srs_msm_batch_partial(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t first,
-                           uint64_t count, bool scalars_mont, G1XYZZ* out);
+                           uint64_t count, uint32_t bucket_lo, uint32_t bucket_hi, bool scalars_mont, G1XYZZ* out);
+uint32_t srs_bucket_count(Srs* s);
 
 struct Proof {
   uint8_t pts[9][64];    // a_1 b_1 c_1 z_1 t_lo t_mid t_hi W_z W_zw  (canonical LE x||y)
@@ -53,6 +54,7 @@ struct Prover {
   // multi-GPU: this rank commits only to SRS powers [shard_first, shard_first + shard_count)
   bool sharded = false;
   uint64_t shard_first = 0, shard_count = 0;
+  uint32_t bucket_lo = 0, bucket_hi = 0xffffffffu;   // bucket-range shard (composes with the point range)
   G1XYZZ partials[9];
 
   enum { QM = 0, QL, QR, QO, QC, S1, S2, S3 };
@@ -62,7 +64,8 @@ struct Prover {
     if (sharded) {
       // point-range shard: leave XYZZ partial sums for the caller's allgather + combine (slot = index of out_xy)
       size_t slot = (size_t)(out_xy - proof.pts[0]) / 64;
-      srs_msm_batch_partial(ctx, srs, d_coeffs, count, shard_first, shard_count, true, partials + slot);
+      srs_msm_batch_partial(ctx, srs, d_coeffs, count, shard_first, shard_count, bucket_lo, bucket_hi, true,
+                            partials + slot);
       return;
     }
     int ident[4] = {0, 0, 0, 0};

@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(ROOT, "build", "host_selftest.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(CSRC, "host_selftest.cpp")
-    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh", "msm_affine.cuh", "modinv.cuh")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh", "msm_bucket.cuh", "modinv.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
                                "-I", CSRC, "-o", out])
@@ -164,55 +164,81 @@ def test_msm_signed_digit_slicing(lib):
             assert sum(d << (c * w) for w, d in enumerate(ds)) == s_, (c, hex(s_))
 
 
-def test_msm_affine_rounds_on_host(lib):
-    """csrc/msm_affine.cuh: the per-thread bodies of the batched-affine bucket accumulation, run round by round on
-    the CPU, against the oracle's affine group law -- bucket shapes 0..37, doubled points, opposite points,
-    identities that travel through later rounds, and every (B, F) blocking incl. ones that split buckets"""
-    rng = random.Random(99)
-    base = [O.g1_multiply(O.G1, rng.randrange(1, O.R_MOD)) for _ in range(24)]
-    table = (ctypes.c_uint32 * (16 * len(base)))()
-    for i, (x, y) in enumerate(base):
+def _pts_buf(points):
+    buf = (ctypes.c_uint32 * (16 * len(points)))()
+    for i, (x, y) in enumerate(points):
         for k in range(8):
-            table[16 * i + k] = (x >> (32 * k)) & 0xFFFFFFFF
-            table[16 * i + 8 + k] = (y >> (32 * k)) & 0xFFFFFFFF
-    P, N = (lambda i: (i, 0)), (lambda i: (i, 1))  # entry = (table index, negated?)
-    buckets = [
-        [], [P(0)], [P(1), P(2)], [P(3), P(3)], [P(4), N(4)], [P(5), N(5), P(6)], [P(6), P(7), P(8), N(8)],
-        [P(9), N(9), P(10), N(10)], [P(11)] * 7, [N(12)] * 8, [P(13), P(13), N(13), N(13), P(14)],
-        [], [], [P(1), N(1), P(1), N(1), P(1), P(2), N(2), P(3), P(3)],
-    ]
-    for size in (3, 5, 16, 31, 37):
-        buckets.append([(rng.randrange(len(base)), rng.randrange(2)) for _ in range(size)])
-    buckets += [[], [N(23)]]
-    entries, offsets = [], [0]
-    for bk in buckets:
-        entries += [i | (s << 31) for i, s in bk]
-        offsets.append(len(entries))
-    expect = []
-    for bk in buckets:
-        acc = None
-        for i, s in bk:
-            acc = O.g1_add(acc, O.g1_neg(base[i]) if s else base[i])
-        expect.append(acc)
-    nb = len(buckets)
-    sorted_arr = (ctypes.c_uint32 * max(1, len(entries)))(*entries)
-    off_arr = (ctypes.c_uint32 * (nb + 1))(*offsets)
-    for B, F in ((1, 1), (2, 3), (3, 64), (5, 2), (8, 8), (32, 32), (1000, 1)):
-        out = (ctypes.c_uint32 * (16 * nb))()
-        inf = (ctypes.c_uint8 * nb)()
-        rounds = lib.hs_msm_affine_rounds(table, len(base), sorted_arr, off_arr, nb, B, F, out, inf)
-        assert rounds == 6  # ceil(log2(37))
-        for b in range(nb):
-            got = None if inf[b] else (unlimbs(out, 2 * b), unlimbs(out, 2 * b + 1))
-            assert got == expect[b], (B, F, b)
-    # nothing to add at all: zero rounds, buckets read straight from the table with their signs
-    off1 = (ctypes.c_uint32 * 4)(0, 1, 1, 2)
-    ent1 = (ctypes.c_uint32 * 2)(5, 7 | (1 << 31))
-    out = (ctypes.c_uint32 * 48)()
-    inf = (ctypes.c_uint8 * 3)()
-    assert lib.hs_msm_affine_rounds(table, len(base), ent1, off1, 3, 4, 4, out, inf) == 0
-    assert (unlimbs(out, 0), unlimbs(out, 1)) == base[5] and inf[1] == 1
-    assert (unlimbs(out, 4), unlimbs(out, 5)) == O.g1_neg(base[7])
+            buf[16 * i + k] = (x >> (32 * k)) & 0xFFFFFFFF
+            buf[16 * i + 8 + k] = (y >> (32 * k)) & 0xFFFFFFFF
+    return buf
+
+
+def _msm_pipeline(lib, points, scalar_vecs, c, fixed, lo, hi, B, g0):
+    n, batch = len(points), len(scalar_vecs)
+    sc = (ctypes.c_uint32 * (8 * n * batch))()
+    for k, vec in enumerate(scalar_vecs):
+        for i, s_ in enumerate(vec):
+            for w in range(8):
+                sc[8 * (k * n + i) + w] = (s_ >> (32 * w)) & 0xFFFFFFFF
+    out = (ctypes.c_uint32 * (16 * batch))()
+    inf = (ctypes.c_uint8 * batch)()
+    rounds = lib.hs_msm_pipeline(_pts_buf(points), n, sc, batch, c, 1 if fixed else 0, lo, hi, B, g0, out, inf)
+    assert rounds >= 1, rounds
+    return [None if inf[k] else (unlimbs(out, 2 * k), unlimbs(out, 2 * k + 1)) for k in range(batch)], rounds
+
+
+def _oracle_msm(points, scalars):
+    acc = None
+    for pt, s_ in zip(points, scalars):
+        if s_ % O.R_MOD:
+            acc = O.g1_add(acc, O.g1_multiply(pt, s_ % O.R_MOD))
+    return acc
+
+
+def test_msm_bucket_pipeline_on_host(lib):
+    """csrc/msm_bucket.cuh + msm_digits.cuh: the whole MSM bucket pipeline (signed digits, padded counting sort, rounds
+    of batched affine additions with the safegcd inversion, recursive bucket reduction, bucket-range shards), every
+    GPU thread body run in a loop on the CPU, against the oracle's group law (curve.py:38-44 semantics)."""
+    rng = random.Random(99)
+    base = [O.g1_multiply(O.G1, rng.randrange(1, O.R_MOD)) for _ in range(12)]
+    # repeated and opposite points: same-bucket collisions exercise doubling, P + (-P) and identities in later rounds
+    points = base + [base[0], base[0], O.g1_neg(base[1]), base[1], base[2], base[2], base[2], O.g1_neg(base[2])]
+    n = len(points)
+    edge = [0, 1, 2, O.R_MOD - 1, O.R_MOD - 2, (1 << 253) + 5, 15, 16, 17, (1 << 128) - 1]
+    rand = lambda: [rng.choice(edge) if rng.random() < 0.3 else rng.randrange(O.R_MOD) for _ in range(n)]
+    # generic mode (one bucket set per window), several blockings
+    for c, B, g0 in ((4, 1, 2), (4, 5, 4), (5, 64, 16), (3, 2, 2)):
+        sc = rand()
+        got, _ = _msm_pipeline(lib, points, [sc], c, False, 0, 1 << 30, B, g0)
+        assert got[0] == _oracle_msm(points, sc), (c, B, g0)
+    # all scalars equal: every window has one heavy bucket (cnt = n = 20 -> 5 rounds), with the collisions above
+    for s_ in (1, 7, O.R_MOD - 1, 0x1111111111111111111111111111111111111111111111111111111111111111 % O.R_MOD):
+        got, rounds = _msm_pipeline(lib, points, [[s_] * n], 4, False, 0, 1 << 30, 3, 4)
+        assert got[0] == _oracle_msm(points, [s_] * n), hex(s_)
+        assert rounds == 5
+    # fixed-base mode: batched scalar vectors share the window table and one bucket set each
+    vecs = [rand(), rand(), [3] * n]
+    expect = [_oracle_msm(points, v) for v in vecs]
+    got, _ = _msm_pipeline(lib, points, vecs, 5, True, 0, 1 << 30, 7, 4)
+    assert got == expect
+    # bucket-range shards (multi-GPU MSM join): the partial sums of disjoint ranges add up to the full result
+    for cuts in ((0, 16), (0, 5, 16), (0, 1, 2, 9, 16), (0, 4, 8, 12, 16)):
+        acc = [None] * len(vecs)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            part, _ = _msm_pipeline(lib, points, vecs, 5, True, lo, hi, 4, 2)
+            acc = [O.g1_add(a, p) for a, p in zip(acc, part)]
+        assert acc == expect, cuts
+    # an empty result: all scalars zero
+    got, _ = _msm_pipeline(lib, points, [[0] * n], 4, False, 0, 1 << 30, 4, 4)
+    assert got == [None]
+    # one bucket with more than 2^12 entries: the rounds past PB_AFF_GRID_ROUNDS (k_aff_tail's share on the GPU)
+    many, cur = [], O.G1
+    for _ in range(4200):
+        many.append(cur)
+        cur = O.g1_add(cur, O.G1)  # i * G: distinct points
+    got, rounds = _msm_pipeline(lib, many, [[5] * len(many)], 4, False, 0, 1 << 30, 16, 16)
+    assert rounds == 13
+    assert got[0] == O.g1_multiply(O.G1, 5 * (4200 * 4201 // 2))
 
 
 @pytest.mark.parametrize("field,p", [(0, O.R_MOD), (1, O.Q_MOD)])
