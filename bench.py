@@ -28,7 +28,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF  # fixed toxic-waste value of the synthetic test SRS
-METRIC = "plonk_proofs_per_s_2^20_gates"
 
 
 def parse():
@@ -38,7 +37,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--seed", type=int, default=20260924, help="seed of the synthetic circuit (7 with --log-n 22 is the "
+                    "circuit of tests/golden/proof_2p22.json)")
     ap.add_argument("--cpu-log-n", type=int, default=8, help="size of the bounded CPU sample (2^k gates)")
+    ap.add_argument("--cpu-fit", default="6,8,10", help="reference arm: sample sizes (log2 gates) of the cost fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0,
                     help="reference arm: worker processes proving independent instances side by side "
@@ -78,12 +80,59 @@ def cpu_sample(log_n, steps=1):
     return n, times
 
 
+def metric_name(log_n):
+    return "plonk_proofs_per_s_2^%d_gates" % log_n
+
+
+def usable_cores():
+    """host threads this process may actually run on: the scheduler affinity mask, capped by the cgroup CPU quota"""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    cores = min(cores, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    cores = min(cores, max(1, quota // period))
+        except Exception:
+            pass
+    return max(1, cores)
+
+
 def _reference_worker(job):
-    """one host process of the reference arm: W warm-up proofs, then K timed ones (module level: spawn-safe)"""
-    log_n, warmup, steps = job
+    """one host process of the reference arm: per step one proof at every sample size (module level: spawn-safe);
+    returns {log_n: [seconds per proof]}"""
+    sizes, warmup, steps = job
     if warmup > 0:
-        cpu_sample(log_n, warmup)
-    return cpu_sample(log_n, max(1, steps))[1]
+        cpu_sample(min(sizes), 1)
+    out = {k: [] for k in sizes}
+    for _ in range(max(1, steps)):
+        for k in sizes:
+            out[k].append(cpu_sample(k, 1)[1][0])
+    return out
+
+
+def fit_cost(points):
+    """least-squares t(n) = a n + b n log2 n (a, b >= 0) through [(n, seconds)]: the commitments are linear in n, the
+    transforms n log n"""
+    import numpy as np
+    A = np.array([[n, n * np.log2(n)] for n, _ in points], dtype=float)
+    y = np.array([t for _, t in points], dtype=float)
+    w = 1.0 / y  # relative errors
+    sol, *_ = np.linalg.lstsq(A * w[:, None], y * w, rcond=None)
+    a, b = float(sol[0]), float(sol[1])
+    if a < 0 or b < 0:  # fall back to the one-parameter fits
+        a1 = float(np.sum(w * w * A[:, 0] * y) / np.sum(w * w * A[:, 0] ** 2))
+        b1 = float(np.sum(w * w * A[:, 1] * y) / np.sum(w * w * A[:, 1] ** 2))
+        a, b = (a1, 0.0) if b < 0 else (0.0, b1)
+    return a, b
 
 
 def reference_arm(args):
@@ -91,11 +140,14 @@ def reference_arm(args):
     if rank != 0:
         return
     # The reference is single-threaded Python, but proofs are independent, so "all the host threads it can use" is
-    # one process per core, each proving its own instance (the CPU counterpart of replicas / proofs in flight).
+    # one process per USABLE core (affinity mask and cgroup quota, not os.cpu_count()), each proving its own
+    # instances (the CPU counterpart of replicas / proofs in flight).
     import multiprocessing as mp
-    procs = min(256, args.cpu_procs if args.cpu_procs > 0 else (os.cpu_count() or 1))
-    n = 1 << args.cpu_log_n
-    job = (args.cpu_log_n, 1 if args.warmup > 0 else 0, args.steps)
+    cores = usable_cores()
+    procs = min(256, args.cpu_procs if args.cpu_procs > 0 else cores)
+    sizes = sorted({int(x) for x in args.cpu_fit.split(",") if x})
+    t_single = cpu_sample(min(8, max(sizes)), 1)[1][0] if procs > 1 else None  # one process alone, for the slowdown
+    job = (sizes, 1 if args.warmup > 0 else 0, args.steps)
     per_proc = None
     if procs > 1:
         try:
@@ -106,22 +158,34 @@ def reference_arm(args):
             procs = 1
     if per_proc is None:
         per_proc = [_reference_worker(job)]
-    t = statistics.mean(x for times in per_proc for x in times)  # seconds per proof inside one process
-    rate = sum(len(times) / sum(times) for times in per_proc)     # sample-size proofs per second, all processes
-    # scale the sample to 2^20 gates: the 9 commitments dominate and are linear in n
-    scale = (1 << args.log_n) / n
-    value = rate / scale
-    sample = "%d processes (one per host core), each running Prover.prove on a 2^%d-gate instance of the same " \
-             "synthetic circuit family (%.2f s per proof and process), scaled linearly in gates to 2^%d" \
-             % (procs, args.cpu_log_n, t, args.log_n)
+    # seconds per proof inside one worker at every sample size, all workers running
+    mean_t = {k: statistics.mean(x for w in per_proc for x in w[k]) for k in sizes}
+    a, b = fit_cost([(1 << k, mean_t[k]) for k in sizes])
+    n_full = 1 << args.log_n
+    t_full = a * n_full + b * n_full * args.log_n          # seconds per 2^log_n-gate proof in one worker
+    value = procs / t_full                                  # all workers
+    k8 = min(8, max(sizes))
+    slowdown = (mean_t[k8] / t_single) if (t_single and k8 in mean_t) else 1.0
+    sample = ("%d worker processes on %d usable host cores (os.cpu_count() = %s), each running the oracle port of "
+              "Prover.prove on 2^{%s}-gate instances of the same synthetic circuit family: %s s per proof and worker; "
+              "cost model t(n) = a n + b n log2 n fitted to those points (a = %.3e, b = %.3e) and EXTRAPOLATED to "
+              "2^%d gates (%.0f s per proof and worker); one worker alone takes %s s at 2^%d gates, i.e. a slowdown "
+              "of %.2fx with all workers running"
+              % (procs, cores, os.cpu_count(), ",".join(str(k) for k in sizes),
+                 ", ".join("%.2f" % mean_t[k] for k in sizes), a, b, args.log_n, t_full,
+                 ("%.2f" % t_single) if t_single else "n/a", k8, slowdown))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.log_n), "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u256 (BN254 Fr/Fq integers)", "data": "synthetic",
+        "extrapolated": True,
         "config": {"workload": "PLONK prove (rounds 1-5, 9 KZG commits), synthetic 2^%d-gate circuit, structured "
                                "test SRS [tau^i]G of 2^%d powers" % (args.log_n, args.log_n),
-                   "log_n": args.log_n, "seed": 20260924, "cpu_sample_log_n": args.cpu_log_n},
-        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": procs, "kind": "port", "sample": sample},
+                   "log_n": args.log_n, "seed": args.seed, "cpu_sample_log_n": sizes},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": procs, "kind": "port", "sample": sample,
+                         "usable_cores": cores, "os_cpu_count": os.cpu_count(), "per_worker_slowdown": slowdown,
+                         "seconds_per_proof_per_worker": {str(k): mean_t[k] for k in sizes},
+                         "fit": {"a_s_per_gate": a, "b_s_per_gate_log_gate": b, "extrapolated_s_per_proof": t_full}},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -222,7 +286,7 @@ def b200_arm(args):
     n = 1 << log_n
     t0 = time.time()
     setup = pb.Setup.generate(TAU, n, ctx=ctx)
-    circ = syn.build_circuit(log_n, seed=20260924, n_public=2)
+    circ = syn.build_circuit(log_n, seed=args.seed, n_public=2)
     pk, A, B, C, public = syn.circuit_arrays(circ)
     K = max(1, args.inflight)
     vp = ctypes.c_void_p
@@ -312,13 +376,22 @@ def b200_arm(args):
     acc_ms, acc_cnt = tot.value, cnt.value
     _lib.check(L.pb200_ctx_timing_read(ctx.handle, 1, ctypes.byref(tot), ctypes.byref(cnt)))
     ntt_ms, ntt_cnt = tot.value, cnt.value
+    _lib.check(L.pb200_ctx_timing_read(ctx.handle, 2, ctypes.byref(tot), ctypes.byref(cnt)))
+    sort_ms = tot.value
+    _lib.check(L.pb200_ctx_timing_read(ctx.handle, 3, ctypes.byref(tot), ctypes.byref(cnt)))
+    red_ms = tot.value
     _lib.check(L.pb200_ctx_timing(ctx.handle, 0))
+    print("[rank %d] per proof (one lane): %.2f ms; MSM sort %.2f, accumulate %.2f, reduce %.2f; NTT passes (main stream) %.2f"
+          % (rank, ms_solo / args.steps, sort_ms / args.steps, acc_ms / args.steps, red_ms / args.steps, ntt_ms / args.steps),
+          file=sys.stderr)
 
     # outside every timed region: byte-for-byte against the oracle's golden proof of this very circuit, when the
     # fixture for this size and seed exists (tests/golden/make_proof_2p20.py; reading a JSON file is not running the
     # oracle).  Reported, not asserted: the parity gate is the test-suite, the bench only says what it saw.
     golden_match = None
-    gpath = os.path.join(ROOT, "tests", "golden", "proof_2p%d_seed20260924.json" % log_n)
+    gpath = os.path.join(ROOT, "tests", "golden", "proof_2p%d_seed%d.json" % (log_n, args.seed))
+    if args.seed == 7:  # the circuits of tests/test_gpu_parity.py's golden proofs
+        gpath = os.path.join(ROOT, "tests", "golden", "proof_2p%d.json" % log_n)
     if os.path.exists(gpath):
         try:
             golden_match = bool(json.load(open(gpath))["proof_hex"] == ref_proof.hex())
@@ -338,79 +411,164 @@ def b200_arm(args):
                         and not vk.verify_proof(n, pb.Proof.from_bytes(bytes(bad)), pub_ints))
         assert verified, "the benchmarked proof does not verify"
 
-    shard_ms = shard_wall_ms = None
+    # ---- N > 1: ONE proof across all the GPUs (north_star's sharded path), checked and timed where the driver's
+    # scaling run sees it: coset slices + slab-sharded interpolation + bucket-sharded commitments, the library's own
+    # NCCL allgathers at the joins (plonkathon_b200/parallel.py, csrc/prover.cu with world > 1)
+    shard = None
     if world > 1:
-        # one proof across all GPUs: point-sharded commitments, one NCCL allgather per round (parallel.py)
         from plonkathon_b200 import parallel
         sp = parallel.ShardedProver.from_arrays(setup, n, pk)  # every rank holds the same circuit instance
         pA, pB, pC = hA.numpy(), hB.numpy(), hC.numpy()  # views of the pinned buffers
-        assert sp.prove_arrays(pA, pB, pC, public) == ref_proof, "sharded proof differs from the single-GPU proof"
+        proof_ok = sp.prove_arrays(pA, pB, pC, public) == ref_proof
+        c0 = parallel.comm_info(ctx)
         barrier()
         t0 = time.perf_counter()
         shard_ms = timed(lambda lane: sp.prove_arrays(pA, pB, pC, public), args.steps, active=lanes[:1],
                          name="one proof sharded across the GPUs") / args.steps
         shard_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        c1 = parallel.comm_info(ctx)
+        # the two sharded operators of BASELINE.json's metric, against their single-GPU results, then timed
+        xs = torch.randint(0, 2 ** 31 - 1, (n, 8), dtype=torch.int32, device="cuda",
+                           generator=torch.Generator(device="cuda").manual_seed(1234))  # same vector on every rank
+        xs[:, 7] &= 0x0FFFFFFF
+        ys, yf = torch.empty_like(xs), torch.empty_like(xs)
+        _lib.check(L.pb200_fr_ntt(ctx.handle, vp(xs.data_ptr()), vp(yf.data_ptr()), log_n, 0))
+        parallel.sharded_ntt(xs, log_n, False, ctx=ctx, out=ys)
+        ctx.sync()
+        ntt_ok = bool(torch.equal(ys, yf))
+        _lib.check(L.pb200_fr_ntt(ctx.handle, vp(xs.data_ptr()), vp(yf.data_ptr()), log_n, 1))
+        parallel.sharded_ntt(xs, log_n, True, ctx=ctx, out=ys)
+        ctx.sync()
+        ntt_ok = ntt_ok and bool(torch.equal(ys, yf))
+        o1, i1 = ctypes.create_string_buffer(64), ctypes.c_int()
+        _lib.check(L.pb200_srs_commit_coeffs(ctx.handle, setup._srs, vp(xs.data_ptr()), n, 0, o1, ctypes.byref(i1)))
+        one = (int.from_bytes(o1.raw[:32], "little"), int.from_bytes(o1.raw[32:], "little"))
+        msm_ok = parallel.sharded_commit(setup, xs, n) == one
+        ok_all = torch.tensor([int(proof_ok), int(ntt_ok), int(msm_ok)], device="cuda")
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)  # true only if true on every rank
+        proof_ok, ntt_ok, msm_ok = (bool(v) for v in ok_all.tolist())
+
+        def ntt_sh(lane=None):
+            parallel.sharded_ntt(xs, log_n, False, ctx=ctx, out=ys)
+            parallel.sharded_ntt(ys, log_n, True, ctx=ctx, out=ys)
+        ntt_sh()
+        ntt_sh_ms = timed(ntt_sh, 5, active=lanes[:1], name="sharded NTT forward + inverse") / 5
+        msm_sh = lambda lane=None: parallel.sharded_commit(setup, xs, n)  # noqa: E731
+        msm_sh()
+        msm_sh_ms = timed(msm_sh, 5, active=lanes[:1], name="sharded commitment") / 5
+        shard = {"ms": shard_ms, "ms_wall_clock": shard_wall_ms, "proof_ok": proof_ok, "ntt_ok": ntt_ok,
+                 "msm_ok": msm_ok, "ntt_pair_ms": ntt_sh_ms, "msm_ms": msm_sh_ms,
+                 "collectives_per_proof": (c1[2] - c0[2]) / args.steps,
+                 "bytes_received_per_proof": (c1[3] - c0[3]) / args.steps}
         del sp
 
-    # component micro-configs (BASELINE.json configs[1], configs[2]), device-timed, rank 0 only
+    # component micro-configs (BASELINE.json configs[1], configs[2], configs[3]), device-timed, rank 0 only
     comp = {}
     if rank == 0:
+        hbm_peak = measured_peaks()[0]
         x = torch.randint(0, 2 ** 31 - 1, (n, 8), dtype=torch.int32, device="cuda")
         x[:, 7] &= 0x0FFFFFFF
         y = torch.empty_like(x)
 
-        def ntt_pair():
-            _lib.check(L.pb200_fr_ntt(ctx.handle, vp(x.data_ptr()), vp(y.data_ptr()), log_n, 0))
-            _lib.check(L.pb200_fr_ntt(ctx.handle, vp(y.data_ptr()), vp(y.data_ptr()), log_n, 1))
-        ntt_pair()
-        ms = timed_local(torch, stream, ntt_pair, 5)
-        hbm_peak = measured_peaks()[0]
-        gbs = 128.0 * n / (ms / 5 * 1e-3) / 1e9  # 64 B per element per transform, two transforms
-        comp["fr_ntt_fwd_plus_inv_2^%d" % log_n] = {
-            "ms": ms / 5, "elems_per_s": 2 * n / (ms / 5 * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                         "modmul_ceiling_frac": (2 * (n / 2 * log_n + n) / (ms / 5 * 1e-3)) / 65.4e9}}
+        def ntt_component(k):
+            m = 1 << k
+            xx = x if m == n else torch.randint(0, 2 ** 31 - 1, (m, 8), dtype=torch.int32, device="cuda")
+            yy = y if m == n else torch.empty_like(xx)
+
+            def pair():
+                _lib.check(L.pb200_fr_ntt(ctx.handle, vp(xx.data_ptr()), vp(yy.data_ptr()), k, 0))
+                _lib.check(L.pb200_fr_ntt(ctx.handle, vp(yy.data_ptr()), vp(yy.data_ptr()), k, 1))
+            pair()
+            ms = timed_local(torch, stream, pair, 5) / 5
+            gbs = 128.0 * m / (ms * 1e-3) / 1e9  # 64 B per element per transform, two transforms
+            return {"ms": ms, "elems_per_s": 2 * m / (ms * 1e-3),
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "modmul_ceiling_frac": (2 * (m / 2 * k + m) / (ms * 1e-3)) / 65.4e9}}
+        comp["fr_ntt_fwd_plus_inv_2^%d" % log_n] = ntt_component(log_n)
+        if log_n + 2 <= 24:
+            comp["fr_ntt_fwd_plus_inv_2^%d" % (log_n + 2)] = ntt_component(log_n + 2)
         ident = ctypes.c_int()
         out = ctypes.create_string_buffer(64)
 
         def commit():
             _lib.check(L.pb200_srs_commit_coeffs(ctx.handle, setup._srs, vp(x.data_ptr()), n, 0, out, ctypes.byref(ident)))
         commit()
-        ms = timed_local(torch, stream, commit, 5)
-        gbs = 96.0 * n / (ms / 5 * 1e-3) / 1e9  # 64 B point + 32 B scalar
+        ms = timed_local(torch, stream, commit, 5) / 5
+        gbs = 96.0 * n / (ms * 1e-3) / 1e9  # 64 B point + 32 B scalar
         comp["g1_msm_fixed_base_2^%d" % log_n] = {
-            "ms": ms / 5, "points_per_s": n / (ms / 5 * 1e-3),
+            "ms": ms, "points_per_s": n / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}}
+        # curve.py:38 ec_lincomb as a drop-in: arbitrary (variable) bases, no precomputed table -- the SRS points themselves
+        pts_dev = torch.from_numpy(setup.export_points_array(0, n)).cuda() if hasattr(setup, "export_points_array") else None
+        if pts_dev is not None:
+            def lincomb():
+                _lib.check(L.pb200_g1_msm(ctx.handle, vp(pts_dev.data_ptr()), vp(x.data_ptr()), n, out, ctypes.byref(ident)))
+            lincomb()
+            ms = timed_local(torch, stream, lincomb, 3) / 3
+            gbs = 96.0 * n / (ms * 1e-3) / 1e9
+            comp["g1_msm_variable_base_2^%d" % log_n] = {
+                "ms": ms, "points_per_s": n / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak}}
+            del pts_dev
+        # BASELINE.json configs[3]: a full Prover.prove at the size of test/mini_poseidon (n = 1024), host buffers
+        small = syn.build_circuit(10, seed=args.seed, n_public=2)
+        spk, sA, sB, sC, spub = syn.circuit_arrays(small)
+        sprover = pb.Prover.from_arrays(setup, 1 << 10, spk)
+        sprover.prove_arrays(sA, sB, sC, spub)
+        ms = timed_local(torch, stream, lambda: sprover.prove_arrays(sA, sB, sC, spub), 10) / 10
+        comp["prove_2^10_gates_latency"] = {"ms": ms, "proofs_per_s": 1e3 / ms,
+                                            "note": "one proof at a time, host buffers, rounds 1-5 + transcript"}
+        del sprover
+        if shard is not None:
+            one_ms = ms_solo / args.steps
+            base_ntt = comp["fr_ntt_fwd_plus_inv_2^%d" % log_n]["ms"]
+            base_msm = comp["g1_msm_fixed_base_2^%d" % log_n]["ms"]
+            comp["sharded_across_%d_gpus" % world] = {
+                "one_proof_ms": shard["ms"], "one_proof_ms_wall_clock": shard["ms_wall_clock"],
+                "one_proof_speedup_vs_1_gpu": one_ms / shard["ms"], "one_proof_efficiency": one_ms / shard["ms"] / world,
+                "fr_ntt_fwd_plus_inv_ms": shard["ntt_pair_ms"], "fr_ntt_elems_per_s": 2 * n / (shard["ntt_pair_ms"] * 1e-3),
+                "fr_ntt_speedup_vs_1_gpu": base_ntt / shard["ntt_pair_ms"],
+                "g1_msm_ms": shard["msm_ms"], "g1_msm_points_per_s": n / (shard["msm_ms"] * 1e-3),
+                "g1_msm_speedup_vs_1_gpu": base_msm / shard["msm_ms"],
+                "collectives_per_proof": shard["collectives_per_proof"],
+                "nvlink_bytes_received_per_proof_and_rank": shard["bytes_received_per_proof"],
+                "note": "ONE proof / transform / commitment across all ranks (strong scaling), max over ranks, device "
+                        "timed; full-vector in, full-vector out on every rank"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    if shard_ms is not None:
-        comp["one_proof_across_%d_gpus_sharded_msm" % world] = {
-            "ms": shard_ms, "ms_wall_clock": shard_wall_ms, "proofs_per_s": 1e3 / shard_ms,
-            "note": "pinned host buffers; commitments point-sharded with one NCCL allgather per round, transforms replicated"}
     hbm_gbs, peak_src = measured_peaks()
     proofs = args.steps * K * world
     value = proofs / (ms_dev * 1e-3)
     e2e = proofs / (ms_e2e * 1e-3)
-    # dominant kernel: MSM bucket accumulation.  Algorithmic bytes: 96 B per point (64 B affine point + 32 B
-    # scalar) x n points per launch (one launch per commitment).
+    # dominant kernel group: the MSM bucket accumulation (rounds of batched affine additions: k_aff_round0 +
+    # k_aff_round launches of one MSM call, bracketed by one event pair).  Algorithmic bytes: 96 B per point (64 B
+    # affine point + 32 B scalar) x the points of the call.
+    xyzz = os.environ.get("PB200_MSM_ACC") == "xyzz"
     acc_avg_ms = acc_ms / max(1, acc_cnt)
-    # 9 commitments x n points per proof go through the accumulation kernel (4 batched launches per proof)
+    # 9 commitments x n points per proof go through the accumulation (4 batched MSM calls per proof)
     points_per_launch = 9.0 * n * args.steps / max(1, acc_cnt)
     achieved = 96.0 * points_per_launch / (acc_avg_ms * 1e-3) / 1e9
-    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/r01_ncu_msm_acc.md:
-    # 5.56 GB for a 3-commitment launch at 2^20), scaled to this run's average launch
-    traffic = 5.557e9 * (points_per_launch / (3.0 * (1 << 20))) if log_n == 20 else None
+    windows = -(-256 // min(21, log_n))
+    # DRAM traffic of the same launches from the committed ncu --set full capture (profiles/r02_dominant_kernel.json,
+    # written by tools/summarize_profiles.py from the .ncu-rep), scaled to this run's average call
+    traffic = None
+    try:
+        dk = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant_kernel.json")))
+        if dk.get("log_n") == log_n and not xyzz:
+            traffic = dk["dram_bytes_per_point"] * points_per_launch
+    except Exception:
+        pass
     ntt_avg_ms = ntt_ms / max(1, ntt_cnt)
     line = {
-        "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(log_n), "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (BN254 Fr/Fq integers, 8x32-bit Montgomery limbs)", "data": "synthetic",
         "config": {"workload": "PLONK prove (rounds 1-5, 9 KZG commits), synthetic 2^%d-gate circuit, structured "
                                "test SRS [tau^i]G of 2^%d powers" % (log_n, log_n),
-                   "log_n": log_n, "seed": 20260924,
+                   "log_n": log_n, "seed": args.seed,
                    "parallelism": ("%d GPUs, replicas" % world if world > 1 else "1 GPU") + ", %d proofs in flight per GPU" % K,
                    "step": "one batch of %d independent proofs per GPU (%d prover lanes: own stream and scratch, shared "
                            "SRS, one host thread each); one lane alone: %.2f ms per proof" % (K, K, ms_solo / args.steps),
@@ -422,17 +580,34 @@ def b200_arm(args):
         "gpu_launches": int(launches),
         "proof_verified": verified,
         "proof_matches_oracle_golden": golden_match,
-        "roofline": {"bound": "hbm", "kernel": "k_msm_seg_accumulate", "achieved": achieved, "peak": hbm_gbs,
+        "sharded_proof_matches_single": shard["proof_ok"] if shard else None,
+        "slab_ntt_matches_single": shard["ntt_ok"] if shard else None,
+        "sharded_msm_matches_single": shard["msm_ok"] if shard else None,
+        "one_proof_sharded": ({"n_gpus": world, "ms": shard["ms"], "proofs_per_s": 1e3 / shard["ms"],
+                               "one_gpu_ms": ms_solo / args.steps,
+                               "speedup": ms_solo / args.steps / shard["ms"],
+                               "strong_scaling_efficiency": ms_solo / args.steps / shard["ms"] / world} if shard else None),
+        "roofline": {"bound": "hbm",
+                     "kernel": "k_msm_seg_accumulate" if xyzz else "k_aff_round0 + k_aff_round (the accumulation rounds of one MSM call)",
+                     "achieved": achieved, "peak": hbm_gbs,
                      "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": 96.0 * points_per_launch,
-                     "modmul_ceiling_frac": (10.0 * 13 * points_per_launch / (acc_avg_ms * 1e-3)) / 65.4e9,
+                     "modmul_ceiling_frac": ((10.0 if xyzz else 6.0) * windows * points_per_launch / (acc_avg_ms * 1e-3)) / 65.4e9,
                      "launches": int(acc_cnt), "avg_launch_ms": acc_avg_ms,
                      "share_of_step": acc_ms / ms_solo if ms_solo else None,
-                     "note": "kernel durations from a pass with one lane (see config.step); integer-pipe bound (ncu: fmaheavy pipe 87% active), not HBM bound; modmul_ceiling_frac = Montgomery "
-                             "products/s of this kernel / 65.4e9 measured peak; traffic is 18x the algorithmic bytes because "
-                             "every point is gathered once per window (13) from the fixed-base table: see DESIGN.md"},
+                     "msm_ms_per_proof": {"sort": sort_ms / args.steps, "accumulate": acc_ms / args.steps,
+                                          "reduce": red_ms / args.steps},
+                     "note": "a 'launch' is one MSM call's accumulation (event pair around its rounds), timed in a pass with "
+                             "one lane (see config.step); integer-pipe bound, not HBM bound (ncu: profiles/); "
+                             "modmul_ceiling_frac = field products/s (6 per affine addition, one addition per point and "
+                             "window) / 65.4e9 measured peak; traffic exceeds the algorithmic bytes because every point "
+                             "is gathered once per window from the fixed-base table: see DESIGN.md"},
         "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "launches": int(ntt_cnt), "avg_launch_ms": ntt_avg_ms,
-                         "note": "main-stream passes only; the coset extensions issued on the side stream are not timed",
+                         "achieved": comp["fr_ntt_fwd_plus_inv_2^%d" % log_n]["roofline"]["achieved"], "peak": hbm_gbs,
+                         "unit": "GB/s", "frac": comp["fr_ntt_fwd_plus_inv_2^%d" % log_n]["roofline"]["frac"],
+                         "note": "achieved = 64 B per element and transform / duration of a 2^%d forward + inverse pair "
+                                 "(components); launches / avg_launch_ms: main-stream passes of the timed proofs (the coset "
+                                 "extensions issued on the side stream are not timed)" % log_n,
                          "share_of_step": ntt_ms / ms_solo if ms_solo else None},
         "components": comp,
         "clocks": sampler.summary(),

@@ -54,19 +54,23 @@ void* pb200_ctx_stream(pb200_ctx* ctx);
 int pb200_fr_to_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n);
 int pb200_fr_from_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n);
 
+/* poly.py:23-109  the ring operations of Polynomial on device-resident canonical vectors of n elements:
+ *   op 0 a + b, 1 a - b, 2 a * b, 3 a / b (element-wise, py_ecc's inv(0) == 0);
+ *   op 4 a + s, 5 a - s, 6 a * s for a Scalar s (h_scalar, canonical) on every element (LAGRANGE basis) --
+ *   Polynomial / Scalar is op 6 with 1/s; op 7 / 8: + s / - s on element 0 only (MONOMIAL basis, poly.py:32-37);
+ *   op 9 shift: out[i] = a[(i + shift) mod n] (poly.py:102-107; not in place).  d_out may alias d_a otherwise. */
+int pb200_fr_vec_op(pb200_ctx* ctx, int op, const void* d_a, const void* d_b, const uint8_t* h_scalar, void* d_out,
+                    uint64_t n, uint64_t shift);
+
 /* poly.py:113-149  Polynomial.fft(inv) / ifft: natural order in and out, n = 2^log_n <= 2^28.
  * inverse != 0 uses the reversed roots and multiplies by n^-1.  d_out may alias d_in. */
 int pb200_fr_ntt(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse);
 int pb200_fr_ntt_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n, int inverse);
 
-/* Multi-GPU slab NTT (poly.py:113-149 across G = 2^log_g GPUs, N = G * 2^log_m):
- *  1. every rank h transforms the decimated sequence x[h::G] locally   -> pb200_fr_ntt_decimated(stride G, offset h)
- *  2. ONE allgather of the G sub-spectra (the caller's NCCL collective) -> d_sub = [G][2^log_m]
- *  3. every rank computes its contiguous output slab X[slab*M .. (slab+1)*M) -> pb200_fr_ntt_slab_combine */
+/* The local building block of the slab-sharded transform: the 2^log_m-point NTT of the strided sub-sequence
+ * d_in[offset + stride * i] (rank h of G transforms x[h::G]). */
 int pb200_fr_ntt_decimated(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_m, int inverse, uint64_t stride,
                            uint64_t offset);
-int pb200_fr_ntt_slab_combine(pb200_ctx* ctx, const void* d_sub, void* d_out, unsigned log_m, unsigned log_g,
-                              uint64_t slab, int inverse);
 
 /* poly.py:156-163  to_coset_extended_lagrange(offset): n Lagrange values -> 4n evaluations on
  * offset * <w_4n>.  h_offset: 32-byte canonical Fr. */
@@ -147,17 +151,49 @@ int pb200_prover_round3(pb200_prover* p, const uint8_t* alpha, const uint8_t* ff
 int pb200_prover_round4(pb200_prover* p, const uint8_t* zeta, uint8_t* h_evals /*6*32*/);             /* :228 */
 int pb200_prover_round5(pb200_prover* p, const uint8_t* v, uint8_t* h_w_xy /*2*64*/);                 /* :241 */
 
-/* ---- multi-GPU MSM join (one process per GPU; the collective itself is the caller's NCCL allgather) ---- */
-/* Restrict every commitment of this prover to the SRS powers [first, first+count) (point-range shard of
- * setup.py:66-72's MSM).  While enabled, the rounds leave XYZZ partial sums (128 bytes each, Montgomery limbs)
- * instead of affine points; slots follow the proof order a b c z t_lo t_mid t_hi W_z W_zw. */
-int pb200_prover_set_shard(pb200_prover* p, uint64_t first, uint64_t count, int enable);
-int pb200_prover_read_partials(pb200_prover* p, unsigned first_slot, unsigned count, uint8_t* h_xyzz);
-/* store combined commitments (canonical x||y little-endian) back into the proof, and serialise it */
-int pb200_prover_set_points(pb200_prover* p, unsigned first_slot, unsigned count, const uint8_t* h_xy);
+/* The round state the reference keeps on `self` (read by its own sanity asserts, prover.py:108-116, 137-145,
+ * 215-219), copied out in canonical form to a device buffer of 2^log_n elements: which = 0 A, 1 B, 2 C, 3 Z, 4 PI
+ * (Lagrange values), 5 T1, 6 T2, 7 T3 (coefficients).  Valid after the round that produces them. */
+int pb200_prover_read_vector(pb200_prover* p, int which, void* d_out);
+/* canonical 768-byte proof of the last rounds run on this prover (Proof.flatten() order, prover.py:18-35) */
 int pb200_prover_serialize(pb200_prover* p, uint8_t* h_proof768);
-/* sum `count` XYZZ partials gathered from all ranks into one canonical affine point (host arithmetic) */
+
+/* ---- multi-GPU: one process per GPU, one communicator per context -------------------------
+ * The library issues its data-path collectives itself, on the context's stream, through NCCL (bound at run time
+ * from the libnccl.so.2 the process has loaded; the single-GPU entry points work without it).  Rendezvous stays
+ * with the caller: one rank draws pb200_comm_unique_id, distributes the 128 bytes (torch.distributed in
+ * plonkathon_b200/parallel.py), every rank calls pb200_comm_init.  2, 4 or 8 ranks of one box. */
+int pb200_comm_unique_id(uint8_t* out128);
+int pb200_comm_init(pb200_ctx* ctx, const uint8_t* id128, int rank, int world);
+/* rank / world of the context (0 / 1 without a communicator), data-path collectives issued so far and the bytes
+ * this rank received in them */
+int pb200_comm_info(pb200_ctx* ctx, int* rank, int* world, uint64_t* collectives, uint64_t* bytes_received);
+/* poly.py:113-149 slab-sharded across the ranks: d_in (2^log_n elements, present on every rank; rank h reads only
+ * x[h::G]) -> d_out (the full transform, on every rank).  Local 2^log_n / G-point transforms with the join twiddle
+ * fused into the store, ONE allgather, then a G-point DFT per element (csrc/ntt_shard.cuh). */
+int pb200_fr_ntt_sharded(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse);
+/* setup.py:66-72's MSM with the 2^(c-1) signed-digit buckets split evenly over the ranks (every rank holds the
+ * coefficients and an SRS replica, walks all digits, but sorts / accumulates / reduces only its buckets); ONE
+ * allgather of 256 bytes per rank at the join; the same affine result on every rank. */
+int pb200_srs_commit_coeffs_sharded(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m,
+                                    int coeffs_montgomery, uint8_t* h_out_xy, int* is_identity);
+/* prover.py:45-49 for one proof across the ranks: as pb200_prover_create, but rank r caches and works on every
+ * G-th point of the 4n coset (coset extensions, selector cache and quotient divide by G), interpolations are
+ * slab-sharded, commitments bucket-sharded.  Every rank calls the prove / round entry points with the same
+ * inputs and gets the same 768 bytes.  A failing check (the reference's asserts) fails on every rank alike. */
+int pb200_prover_create_sharded(pb200_ctx* ctx, pb200_srs* srs, unsigned log_n, const uint8_t* const* h_pk,
+                                pb200_prover** out);
+/* Operator-level shards with a caller-side join (tests, other transports): the partial sum over the SRS powers
+ * [first, first+count) and the bucket magnitudes [bucket_lo, bucket_hi) of pb200_srs_bucket_count's range, as one
+ * XYZZ point (128 bytes, Montgomery limbs); pb200_g1_combine_partials_host adds such partials. */
+int pb200_srs_commit_partial(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t first, uint64_t count,
+                             uint32_t bucket_lo, uint32_t bucket_hi, int coeffs_montgomery, uint8_t* h_xyzz128);
+int pb200_srs_bucket_count(pb200_srs* srs, uint32_t* out);
 int pb200_g1_combine_partials_host(const uint8_t* h_xyzz, unsigned count, uint8_t* h_out_xy, int* is_identity);
+/* the host half of the sharded commitment's join: h_sr = [world][sets] pairs (S = sum of the rank's buckets,
+ * R = sum_j (j+1) B_j over them; 2 x 128 bytes XYZZ); rank rho owns buckets [rho * nloc, (rho+1) * nloc) */
+int pb200_g1_join_bucket_shards_host(const uint8_t* h_sr, unsigned world, unsigned sets, uint32_t nloc, uint8_t* h_out_xy,
+                                     int* is_identity);
 
 /* ---- Transcript (transcript.py:58-123; host code) ---------------------------------------------- */
 int pb200_transcript_create(const uint8_t* label, size_t label_len, pb200_transcript** out);

@@ -41,7 +41,17 @@ def _load():
         "pb200_fr_ntt": (I, [V, V, V, U, I]),
         "pb200_fr_ntt_host": (I, [V, V, V, U, I]),
         "pb200_fr_ntt_decimated": (I, [V, V, V, U, I, U64, U64]),
-        "pb200_fr_ntt_slab_combine": (I, [V, V, V, U, U, U64, I]),
+        "pb200_fr_ntt_sharded": (I, [V, V, V, U, I]),
+        "pb200_fr_vec_op": (I, [V, I, V, V, V, V, U64, U64]),
+        "pb200_prover_read_vector": (I, [V, I, V]),
+        "pb200_comm_unique_id": (I, [V]),
+        "pb200_comm_init": (I, [V, V, I, I]),
+        "pb200_comm_info": (I, [V, P(I), P(I), P(U64), P(U64)]),
+        "pb200_srs_commit_coeffs_sharded": (I, [V, V, V, U64, I, V, P(I)]),
+        "pb200_prover_create_sharded": (I, [V, V, U, V, P(V)]),
+        "pb200_srs_commit_partial": (I, [V, V, V, U64, U64, U, U, I, V]),
+        "pb200_srs_bucket_count": (I, [V, P(U)]),
+        "pb200_g1_join_bucket_shards_host": (I, [V, U, U, U, V, P(I)]),
         "pb200_fr_coset_extend": (I, [V, V, V, U, V]),
         "pb200_fr_coset_extend_host": (I, [V, V, V, U, V]),
         "pb200_fr_coset_to_coeffs": (I, [V, V, V, U, V]),
@@ -69,9 +79,6 @@ def _load():
         "pb200_prover_round3": (I, [V, V, V, V]),
         "pb200_prover_round4": (I, [V, V, V]),
         "pb200_prover_round5": (I, [V, V, V]),
-        "pb200_prover_set_shard": (I, [V, U64, U64, I]),
-        "pb200_prover_read_partials": (I, [V, U, U, V]),
-        "pb200_prover_set_points": (I, [V, U, U, V]),
         "pb200_prover_serialize": (I, [V, V]),
         "pb200_g1_combine_partials_host": (I, [V, U, V, P(I)]),
         "pb200_transcript_create": (I, [V, ctypes.c_size_t, P(V)]),

@@ -4,6 +4,8 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "comm.cuh"
+#include "msm_bucket.cuh"
 #include "prover.cuh"
 #include "pairing.cuh"
 #include "transcript.cuh"
@@ -16,10 +18,12 @@ void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& 
 Fr fr_from_u64(uint64_t x);
 void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
                      const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
-void ntt_slab_combine(Context* ctx, const Fr* sub, Fr* out, int log_m, int log_g, uint64_t slab, bool inverse);
+void ntt_sharded(Context* ctx, const Fr* const* in, Fr* const* out, int count, int log_n, bool inverse);
 // poly_ops.cu
 void fr_to_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
 void fr_from_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n);
+void fr_vec_op(Context* ctx, int op, const Fr* a, const Fr* b, const Fr& scalar_canonical, Fr* out, uint64_t n,
+               uint64_t shift);
 void barycentric_eval(Context* ctx, const Fr* d_vals, int log_n, const Fr& x_mont, Fr* h_out);
 float bench_modmul(Context* ctx, int field, uint64_t threads, uint32_t iters);
 // msm.cu
@@ -36,7 +40,7 @@ void msm_run(Context* ctx, const G1Affine* points, uint64_t n, const Fr* scalars
              bool fixed_base, uint64_t point_stride, uint8_t* out_xy, int* is_identity);
 void affine_to_mont(Context* ctx, const G1Affine* in, G1Affine* out, uint64_t n);
 // prover.cu
-Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk);
+Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk, bool sharded);
 void prover_destroy(Prover* p);
 void prover_prove(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_t* hC, const uint8_t* h_public,
                   uint64_t n_public, uint8_t* out768, bool wires_on_device);
@@ -46,9 +50,9 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c);
 void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c);
 void prover_round4(Prover* P, const Fr& zeta_c);
 void prover_round5(Prover* P, const Fr& v_c);
-void prover_set_shard(Prover* P, uint64_t first, uint64_t count, bool enable);
 void prover_serialize(const Prover* P, uint8_t* out768);
 void g1_combine_partials_host(const G1XYZZ* parts, uint32_t count, uint8_t* out_xy, int* is_identity);
+void host_join_bucket_shards(const SR* all, uint32_t world, uint32_t sets, uint32_t nloc, G1XYZZ* out);
 }  // namespace pb200
 
 using namespace pb200;
@@ -69,6 +73,20 @@ static thread_local std::string g_err;
   }
 
 static Context* C(pb200_ctx* c) { return reinterpret_cast<Context*>(c); }
+
+// Every entry point that touches the GPU runs on its context's device, whatever device the calling host thread had
+// current (contexts on several GPUs in one process, provers driven from worker threads); the previous device is
+// restored on the way out.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const Context* c) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != c->device) { cudaSetDevice(c->device); prev = cur; }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define PB_ON_CTX(c) DeviceGuard guard__(c)
 
 static Fr load_fr_canonical(const uint8_t* h) {
   Fr a;
@@ -118,7 +136,7 @@ void pb200_ctx_destroy(pb200_ctx* ctx) {
 }
 
 int pb200_ctx_sync(pb200_ctx* ctx) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CUDA(cudaStreamSynchronize(C(ctx)->stream));
   PB_API_END
 }
@@ -126,7 +144,7 @@ int pb200_ctx_sync(pb200_ctx* ctx) {
 uint64_t pb200_ctx_launches(pb200_ctx* ctx) { return C(ctx)->launches; }
 
 int pb200_ctx_timing(pb200_ctx* ctx, int enable) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   Context* c = C(ctx);
   PB_CUDA(cudaStreamSynchronize(c->stream));
   for (auto& v : c->timed) {
@@ -137,7 +155,7 @@ int pb200_ctx_timing(pb200_ctx* ctx, int enable) {
   PB_API_END
 }
 int pb200_ctx_timing_read(pb200_ctx* ctx, int category, double* total_ms, uint64_t* count) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   Context* c = C(ctx);
   PB_CHECK(category >= 0 && category < 4, "bad timing category");
   PB_CUDA(cudaStreamSynchronize(c->stream));
@@ -154,35 +172,68 @@ int pb200_ctx_timing_read(pb200_ctx* ctx, int category, double* total_ms, uint64
 void* pb200_ctx_stream(pb200_ctx* ctx) { return (void*)C(ctx)->stream; }
 
 int pb200_fr_to_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   fr_to_mont(C(ctx), (const Fr*)d_in, (Fr*)d_out, n);
   PB_API_END
 }
 int pb200_fr_from_mont(pb200_ctx* ctx, const void* d_in, void* d_out, uint64_t n) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   fr_from_mont(C(ctx), (const Fr*)d_in, (Fr*)d_out, n);
   PB_API_END
 }
 
+int pb200_fr_vec_op(pb200_ctx* ctx, int op, const void* d_a, const void* d_b, const uint8_t* h_scalar, void* d_out,
+                    uint64_t n, uint64_t shift) {
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  Fr s = Fr::zero();
+  if (h_scalar) s = load_fr_canonical(h_scalar);
+  PB_CHECK(op < 4 ? d_b != nullptr : true, "missing second operand");
+  fr_vec_op(C(ctx), op, (const Fr*)d_a, (const Fr*)d_b, s, (Fr*)d_out, n, shift);
+  PB_API_END
+}
+
 int pb200_fr_ntt(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   ntt_run(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, inverse != 0, (uint64_t)1 << log_n, nullptr, nullptr);
   PB_API_END
 }
 
 int pb200_fr_ntt_decimated(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_m, int inverse, uint64_t stride,
                            uint64_t offset) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CHECK(stride >= 1, "bad stride");
   ntt_run_strided(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_m, inverse != 0, (uint64_t)1 << log_m, nullptr, nullptr,
                   stride, offset);
   PB_API_END
 }
-int pb200_fr_ntt_slab_combine(pb200_ctx* ctx, const void* d_sub, void* d_out, unsigned log_m, unsigned log_g,
-                              uint64_t slab, int inverse) {
+int pb200_fr_ntt_sharded(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, int inverse) {
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  const Fr* in = (const Fr*)d_in;
+  Fr* out = (Fr*)d_out;
+  ntt_sharded(C(ctx), &in, &out, 1, (int)log_n, inverse != 0);
+  PB_API_END
+}
+
+// ---- communicator ---------------------------------------------------------------------------------------------
+int pb200_comm_unique_id(uint8_t* out128) {
   PB_API_BEGIN
-  PB_CHECK(log_g >= 1 && log_g <= 3 && slab < ((uint64_t)1 << log_g), "slab NTT supports 2, 4 or 8 ranks");
-  ntt_slab_combine(C(ctx), (const Fr*)d_sub, (Fr*)d_out, (int)log_m, (int)log_g, slab, inverse != 0);
+  comm_unique_id(out128);
+  PB_API_END
+}
+int pb200_comm_init(pb200_ctx* ctx, const uint8_t* id128, int rank, int world) {
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  Context* c = C(ctx);
+  PB_CHECK(!c->comm, "this context already has a communicator");
+  c->comm = comm_create(id128, rank, world);
+  PB_API_END
+}
+int pb200_comm_info(pb200_ctx* ctx, int* rank, int* world, uint64_t* collectives, uint64_t* bytes_received) {
+  PB_API_BEGIN
+  Context* c = C(ctx);
+  *rank = c->comm ? c->comm->rank : 0;
+  *world = c->comm ? c->comm->world : 1;
+  *collectives = c->comm ? c->comm->collectives : 0;
+  *bytes_received = c->comm ? c->comm->bytes_gathered : 0;
   PB_API_END
 }
 
@@ -200,7 +251,7 @@ struct HostStage {
 };
 
 int pb200_fr_ntt_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n, int inverse) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   size_t bytes = ((size_t)1 << log_n) * 32;
   HostStage st(C(ctx), h_in, bytes, bytes);
   ntt_run(C(ctx), st.in.as<Fr>(), st.out.as<Fr>(), (int)log_n, inverse != 0, (uint64_t)1 << log_n, nullptr, nullptr);
@@ -231,13 +282,13 @@ static void coset_to_coeffs(Context* ctx, const Fr* d_in, Fr* d_out, int log_n, 
 }
 
 int pb200_fr_coset_extend(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   coset_extend(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, h_offset);
   PB_API_END
 }
 int pb200_fr_coset_extend_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n,
                                const uint8_t* h_offset) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   size_t bytes = ((size_t)1 << log_n) * 32;
   HostStage st(C(ctx), h_in, bytes, bytes * 4);
   coset_extend(C(ctx), st.in.as<Fr>(), st.out.as<Fr>(), (int)log_n, h_offset);
@@ -245,13 +296,13 @@ int pb200_fr_coset_extend_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_o
   PB_API_END
 }
 int pb200_fr_coset_to_coeffs(pb200_ctx* ctx, const void* d_in, void* d_out, unsigned log_n, const uint8_t* h_offset) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   coset_to_coeffs(C(ctx), (const Fr*)d_in, (Fr*)d_out, (int)log_n, h_offset);
   PB_API_END
 }
 int pb200_fr_coset_to_coeffs_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* h_out, unsigned log_n,
                                   const uint8_t* h_offset) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   size_t bytes = ((size_t)1 << log_n) * 32;
   HostStage st(C(ctx), h_in, bytes, bytes);
   coset_to_coeffs(C(ctx), st.in.as<Fr>(), st.out.as<Fr>(), (int)log_n, h_offset);
@@ -260,7 +311,7 @@ int pb200_fr_coset_to_coeffs_host(pb200_ctx* ctx, const uint8_t* h_in, uint8_t* 
 }
 
 int pb200_fr_barycentric_eval(pb200_ctx* ctx, const void* d_vals, unsigned log_n, const uint8_t* h_x, uint8_t* h_out) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   Fr x = fp_to_mont(load_fr_canonical(h_x));
   Fr r;
   barycentric_eval(C(ctx), (const Fr*)d_vals, (int)log_n, x, &r);
@@ -269,7 +320,7 @@ int pb200_fr_barycentric_eval(pb200_ctx* ctx, const void* d_vals, unsigned log_n
 }
 int pb200_fr_barycentric_eval_host(pb200_ctx* ctx, const uint8_t* h_vals, unsigned log_n, const uint8_t* h_x,
                                    uint8_t* h_out) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   size_t bytes = ((size_t)1 << log_n) * 32;
   HostStage st(C(ctx), h_vals, bytes, 0);
   Fr x = fp_to_mont(load_fr_canonical(h_x));
@@ -281,7 +332,7 @@ int pb200_fr_barycentric_eval_host(pb200_ctx* ctx, const uint8_t* h_vals, unsign
 
 int pb200_g1_msm(pb200_ctx* ctx, const void* d_points, const void* d_scalars, uint64_t n, uint8_t* h_out_xy,
                  int* is_identity) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CHECK(n > 0, "ec_lincomb of an empty list (the reference raises ValueError, curve.py:93)");
   Context* c = C(ctx);
   DevBuf mont(n * sizeof(G1Affine));
@@ -293,7 +344,7 @@ int pb200_g1_msm(pb200_ctx* ctx, const void* d_points, const void* d_scalars, ui
 
 int pb200_g1_msm_host(pb200_ctx* ctx, const uint8_t* h_points, const uint8_t* h_scalars, uint64_t n,
                       uint8_t* h_out_xy, int* is_identity) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CHECK(n > 0, "ec_lincomb of an empty list (the reference raises ValueError, curve.py:93)");
   Context* c = C(ctx);
   DevBuf pts(n * 64), sc(n * 32);
@@ -305,32 +356,32 @@ int pb200_g1_msm_host(pb200_ctx* ctx, const uint8_t* h_points, const uint8_t* h_
 }
 
 int pb200_srs_create(pb200_ctx* ctx, const uint8_t* h_points, uint64_t n, int precompute, pb200_srs** out) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CHECK(n > 0, "empty SRS");
   *out = reinterpret_cast<pb200_srs*>(srs_create(C(ctx), h_points, n, precompute));
   PB_API_END
 }
 int pb200_srs_generate(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CHECK(n > 0, "empty SRS");
   *out = reinterpret_cast<pb200_srs*>(srs_generate(C(ctx), load_fr_canonical(h_tau), n, precompute));
   PB_API_END
 }
 int pb200_srs_generate_lagrange(pb200_ctx* ctx, const uint8_t* h_tau, uint64_t n, int precompute, pb200_srs** out) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   PB_CHECK(n > 0, "empty SRS");
   *out = reinterpret_cast<pb200_srs*>(srs_generate_lagrange(C(ctx), load_fr_canonical(h_tau), n, precompute));
   PB_API_END
 }
 int pb200_srs_commit_coeffs_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t* h_coeffs, uint64_t m,
                                  uint8_t* h_out_xy, int* is_identity) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   HostStage st(C(ctx), h_coeffs, (size_t)m * 32, 0);
   srs_msm(C(ctx), reinterpret_cast<Srs*>(srs), (const Fr*)st.in.p, m, false, h_out_xy, is_identity);
   PB_API_END
 }
 int pb200_srs_export(pb200_ctx* ctx, pb200_srs* srs, uint8_t* h_points, uint64_t first, uint64_t count) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   srs_export(C(ctx), reinterpret_cast<Srs*>(srs), h_points, first, count);
   PB_API_END
 }
@@ -339,7 +390,7 @@ uint64_t pb200_srs_size(pb200_srs* srs) { return srs_size(reinterpret_cast<Srs*>
 
 int pb200_srs_commit_lagrange(pb200_ctx* ctx, pb200_srs* srs, const void* d_values, unsigned log_n, uint8_t* h_out_xy,
                               int* is_identity) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   Context* c = C(ctx);
   uint64_t n = (uint64_t)1 << log_n;
   PB_CHECK(n <= srs_size(reinterpret_cast<Srs*>(srs)), "Not enough powers in setup");
@@ -350,7 +401,7 @@ int pb200_srs_commit_lagrange(pb200_ctx* ctx, pb200_srs* srs, const void* d_valu
 }
 int pb200_srs_commit_lagrange_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t* h_values, unsigned log_n,
                                    uint8_t* h_out_xy, int* is_identity) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   size_t bytes = ((size_t)1 << log_n) * 32;
   HostStage st(C(ctx), h_values, bytes, 0);
   int rc = pb200_srs_commit_lagrange(ctx, srs, st.in.p, log_n, h_out_xy, is_identity);
@@ -359,88 +410,91 @@ int pb200_srs_commit_lagrange_host(pb200_ctx* ctx, pb200_srs* srs, const uint8_t
 }
 int pb200_srs_commit_coeffs(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m, int coeffs_montgomery,
                             uint8_t* h_out_xy, int* is_identity) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   srs_msm(C(ctx), reinterpret_cast<Srs*>(srs), (const Fr*)d_coeffs, m, coeffs_montgomery != 0, h_out_xy, is_identity);
   PB_API_END
 }
 
 int pb200_prover_create(pb200_ctx* ctx, pb200_srs* srs, unsigned log_n, const uint8_t* const* h_pk,
                         pb200_prover** out) {
-  PB_API_BEGIN
-  *out = reinterpret_cast<pb200_prover*>(prover_create(C(ctx), reinterpret_cast<Srs*>(srs), (int)log_n, h_pk));
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  *out = reinterpret_cast<pb200_prover*>(prover_create(C(ctx), reinterpret_cast<Srs*>(srs), (int)log_n, h_pk, false));
+  PB_API_END
+}
+int pb200_prover_create_sharded(pb200_ctx* ctx, pb200_srs* srs, unsigned log_n, const uint8_t* const* h_pk,
+                                pb200_prover** out) {
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  *out = reinterpret_cast<pb200_prover*>(prover_create(C(ctx), reinterpret_cast<Srs*>(srs), (int)log_n, h_pk, true));
   PB_API_END
 }
 void pb200_prover_destroy(pb200_prover* p) { prover_destroy(reinterpret_cast<Prover*>(p)); }
 
 int pb200_prover_prove(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
                        const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   prover_prove(reinterpret_cast<Prover*>(p), h_A, h_B, h_C, h_public, n_public, h_proof768, false);
   PB_API_END
 }
 int pb200_prover_prove_device(pb200_prover* p, const void* d_A, const void* d_B, const void* d_C,
                               const uint8_t* h_public, uint64_t n_public, uint8_t* h_proof768) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   prover_prove(reinterpret_cast<Prover*>(p), (const uint8_t*)d_A, (const uint8_t*)d_B, (const uint8_t*)d_C, h_public,
                n_public, h_proof768, true);
   PB_API_END
 }
 int pb200_prover_round1(pb200_prover* p, const uint8_t* h_A, const uint8_t* h_B, const uint8_t* h_C,
                         const uint8_t* h_public, uint64_t n_public, uint8_t* h_abc_xy) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   Prover* P = reinterpret_cast<Prover*>(p);
   prover_round1(P, h_A, h_B, h_C, h_public, n_public, false);
   memcpy(h_abc_xy, P->proof.pts[0], 3 * 64);
   PB_API_END
 }
 int pb200_prover_round2(pb200_prover* p, const uint8_t* beta, const uint8_t* gamma, uint8_t* h_z_xy) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   Prover* P = reinterpret_cast<Prover*>(p);
   prover_round2(P, load_fr_canonical(beta), load_fr_canonical(gamma));
   memcpy(h_z_xy, P->proof.pts[3], 64);
   PB_API_END
 }
 int pb200_prover_round3(pb200_prover* p, const uint8_t* alpha, const uint8_t* fft_cofactor, uint8_t* h_t_xy) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   Prover* P = reinterpret_cast<Prover*>(p);
   prover_round3(P, load_fr_canonical(alpha), load_fr_canonical(fft_cofactor));
   memcpy(h_t_xy, P->proof.pts[4], 3 * 64);
   PB_API_END
 }
 int pb200_prover_round4(pb200_prover* p, const uint8_t* zeta, uint8_t* h_evals) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   Prover* P = reinterpret_cast<Prover*>(p);
   prover_round4(P, load_fr_canonical(zeta));
   memcpy(h_evals, P->proof.evals[0], 6 * 32);
   PB_API_END
 }
 int pb200_prover_round5(pb200_prover* p, const uint8_t* v, uint8_t* h_w_xy) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   Prover* P = reinterpret_cast<Prover*>(p);
   prover_round5(P, load_fr_canonical(v));
   memcpy(h_w_xy, P->proof.pts[7], 2 * 64);
   PB_API_END
 }
 
-int pb200_prover_set_shard(pb200_prover* p, uint64_t first, uint64_t count, int enable) {
-  PB_API_BEGIN
-  prover_set_shard(reinterpret_cast<Prover*>(p), first, count, enable != 0);
-  PB_API_END
-}
-int pb200_prover_read_partials(pb200_prover* p, unsigned first_slot, unsigned count, uint8_t* h_xyzz) {
-  PB_API_BEGIN
-  PB_CHECK(first_slot + count <= 9, "proof has 9 commitment slots");
-  memcpy(h_xyzz, reinterpret_cast<Prover*>(p)->partials + first_slot, (size_t)count * sizeof(G1XYZZ));
-  PB_API_END
-}
-int pb200_prover_set_points(pb200_prover* p, unsigned first_slot, unsigned count, const uint8_t* h_xy) {
-  PB_API_BEGIN
-  PB_CHECK(first_slot + count <= 9, "proof has 9 commitment slots");
-  memcpy(reinterpret_cast<Prover*>(p)->proof.pts[first_slot], h_xy, (size_t)count * 64);
+int pb200_prover_read_vector(pb200_prover* p, int which, void* d_out) {
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
+  Prover* P = reinterpret_cast<Prover*>(p);
+  const Fr* src = nullptr;
+  switch (which) {
+    case 0: case 1: case 2: case 3: src = P->lag[which].as<Fr>(); break;   // A B C Z, Lagrange values
+    case 4: src = P->pi_lag.as<Fr>(); break;                               // PI, Lagrange values
+    case 5: case 6: case 7: src = P->tq.as<Fr>() + (uint64_t)(which - 5) * P->n; break;  // T1 T2 T3, coefficients
+    default: PB_CHECK(false, "unknown prover vector");
+  }
+  fr_from_mont(P->ctx, src, (Fr*)d_out, P->n);
+  PB_CUDA(cudaStreamSynchronize(P->ctx->stream));
   PB_API_END
 }
 int pb200_prover_serialize(pb200_prover* p, uint8_t* h_proof768) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(reinterpret_cast<Prover*>(p)->ctx);
   prover_serialize(reinterpret_cast<Prover*>(p), h_proof768);
   PB_API_END
 }
@@ -449,6 +503,39 @@ int pb200_g1_combine_partials_host(const uint8_t* h_xyzz, unsigned count, uint8_
   std::vector<G1XYZZ> parts(count);
   memcpy(parts.data(), h_xyzz, (size_t)count * sizeof(G1XYZZ));
   g1_combine_partials_host(parts.data(), count, h_out_xy, is_identity);
+  PB_API_END
+}
+
+int pb200_srs_commit_partial(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t first, uint64_t count,
+                             uint32_t bucket_lo, uint32_t bucket_hi, int coeffs_montgomery, uint8_t* h_xyzz128) {
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  const Fr* sc = (const Fr*)d_coeffs;
+  G1XYZZ part;
+  srs_msm_batch_partial(C(ctx), reinterpret_cast<Srs*>(srs), &sc, 1, first, count, bucket_lo, bucket_hi,
+                        coeffs_montgomery != 0, &part);
+  memcpy(h_xyzz128, &part, sizeof(part));
+  PB_API_END
+}
+int pb200_srs_bucket_count(pb200_srs* srs, uint32_t* out) {
+  PB_API_BEGIN
+  *out = srs_bucket_count(reinterpret_cast<Srs*>(srs));
+  PB_API_END
+}
+int pb200_srs_commit_coeffs_sharded(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeffs, uint64_t m,
+                                    int coeffs_montgomery, uint8_t* h_out_xy, int* is_identity) {
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
+  const Fr* sc = (const Fr*)d_coeffs;
+  srs_msm_batch_sharded(C(ctx), reinterpret_cast<Srs*>(srs), &sc, 1, m, coeffs_montgomery != 0, h_out_xy, is_identity);
+  PB_API_END
+}
+int pb200_g1_join_bucket_shards_host(const uint8_t* h_sr, unsigned world, unsigned sets, uint32_t nloc, uint8_t* h_out_xy,
+                                     int* is_identity) {
+  PB_API_BEGIN
+  std::vector<SR> all((size_t)world * sets);
+  memcpy(all.data(), h_sr, all.size() * sizeof(SR));
+  std::vector<G1XYZZ> ws(sets);
+  host_join_bucket_shards(all.data(), world, sets, nloc, ws.data());
+  for (unsigned k = 0; k < sets; k++) g1_combine_partials_host(&ws[k], 1, h_out_xy + 64 * k, is_identity + k);
   PB_API_END
 }
 
@@ -544,7 +631,7 @@ int pb200_g2_add(const uint8_t* h_p, int p_identity, const uint8_t* h_q, int q_i
 }
 
 int pb200_bench_modmul(pb200_ctx* ctx, int field, uint64_t threads, uint32_t iters, float* ms_out) {
-  PB_API_BEGIN
+  PB_API_BEGIN PB_ON_CTX(C(ctx));
   *ms_out = bench_modmul(C(ctx), field, threads, iters);
   PB_API_END
 }

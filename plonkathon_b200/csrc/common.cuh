@@ -11,6 +11,7 @@
 
 #include "curve.cuh"
 #include "field.cuh"
+#include "modinv.cuh"
 
 namespace pb200 {
 
@@ -64,6 +65,8 @@ struct DevBuf {
 
 struct NttPlan;
 struct Srs;
+struct Comm;
+struct ShardTables;
 
 struct Context {
   int device = 0;
@@ -77,6 +80,9 @@ struct Context {
   std::map<int, std::unique_ptr<NttPlan>> plans;  // key: log_n * 2 + inverse
   DevBuf scratch[8];                               // reusable temporaries
   DevBuf msm_aff[6];                               // batched-affine bucket accumulation (msm.cu)
+  Comm* comm = nullptr;                            // multi-GPU: this rank's communicator (comm.cuh), or null
+  DevBuf gather;                                   // receive buffer of the sharded transforms' allgather
+  std::map<int, std::unique_ptr<ShardTables>> shard_tables;  // per (log_n, inverse): twiddles of the sharded NTT join
   uint64_t launches = 0;                           // kernels launched through this context
   // optional per-kernel timing (bench.py roofline): CUDA event pairs on the launching stream
   bool timing = false;

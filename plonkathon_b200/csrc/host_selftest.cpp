@@ -126,7 +126,7 @@ int hs_curve_op(int op, const uint32_t* acc_in, const uint32_t* other, int other
 // vector: the rank's partial sum.  Returns the number of accumulation rounds that did work, -1 on bad input.
 int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars, uint32_t batch, uint32_t c,
                     int fixed_base, uint32_t lo, uint32_t hi, uint32_t B, uint32_t g0, uint32_t* out, uint8_t* out_inf) {
-  if (!n || !batch || batch > 4 || (!fixed_base && batch != 1) || c < 1 || c > 16 || B < 1 || B > PB_AFF_BMAX) return -1;
+  if (!n || !batch || batch > 4 || (!fixed_base && batch != 1) || c < 1 || c > 16 || B < 2 || B > PB_AFF_BMAX) return -1;
   if (g0 < 2 || (g0 & (g0 - 1))) return -1;
   MsmGeom g;
   g.c = c;
@@ -212,20 +212,37 @@ int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars,
   }
   // reduction
   ReduceArgs ra;
-  ra.pts = pts.data(); ra.off = off.data(); ra.cnt = counts.data(); ra.xb = nullptr; ra.in = nullptr;
-  ra.sets = g.sets; ra.m = g.nloc; ra.g = g0; ra.log_G = 0;
+  ra.pts = pts.data(); ra.off = off.data(); ra.cnt = counts.data(); ra.xb = nullptr;
+  ra.sets = g.sets; ra.m = g.nloc; ra.g = g0;
   std::vector<SR> cur((size_t)g.sets * reduce_groups(ra.m, ra.g)), nxt;
   ra.out = cur.data();
   for (uint64_t t = 0; t < cur.size() + 3; t++) reduce_level0_thread(ra, t);
   uint32_t m = reduce_groups(ra.m, ra.g), log_G = 0;
   while ((1u << log_G) < g0) log_G++;
-  ra.pts = nullptr;
   while (m > 1) {
-    nxt.assign((size_t)g.sets * reduce_groups(m, 4), SR());
-    ra.in = cur.data(); ra.out = nxt.data(); ra.m = m; ra.g = 4; ra.log_G = log_G;  // g = 4: more levels per test
-    for (uint64_t t = 0; t < nxt.size() + 3; t++) reduce_level_thread(ra, t);
-    m = reduce_groups(m, 4);
-    log_G += 2;
+    // the block-wide level (k_reduce_block in msm.cu), its phases run thread by thread
+    const uint32_t chunks = reduce_chunks(m);
+    nxt.assign((size_t)g.sets * chunks, SR());
+    BlockLevelArgs ba;
+    ba.in = cur.data(); ba.out = nxt.data(); ba.sets = g.sets; ba.m = m; ba.log_G = log_G;
+    for (uint32_t set = 0; set < g.sets; set++)
+      for (uint32_t chunk = 0; chunk < chunks; chunk++) {
+        std::vector<G1XYZZ> sh(256), xs(256), tmp(256);
+        for (uint32_t t = 0; t < 256; t++) blk_local(ba, set, chunk, t, sh[t], xs[t]);
+        for (uint32_t d = 1; d < 256; d <<= 1) {
+          for (uint32_t t = 0; t < 256; t++) tmp[t] = blk_scan_step(sh.data(), t, d);
+          sh = tmp;
+        }
+        const G1XYZZ s_total = sh[0];
+        for (uint32_t t = 0; t < 256; t++) tmp[t] = blk_weight(ba, t, xs[t], sh[t]);
+        sh = tmp;
+        for (uint32_t d = 128; d > 0; d >>= 1)
+          for (uint32_t t = 0; t < 256; t++) blk_tree_step(sh.data(), t, d);
+        nxt[(size_t)set * chunks + chunk].S = s_total;
+        nxt[(size_t)set * chunks + chunk].R = sh[0];
+      }
+    m = chunks;
+    log_G += 10;
     cur.swap(nxt);
   }
   std::vector<G1XYZZ> ws(g.sets);

@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "msm_bucket.cuh"
 #include "msm_digits.cuh"
 
@@ -300,8 +301,34 @@ __global__ void __launch_bounds__(128) k_msm_stitch_heavy(const G1XYZZ* slots, c
 __global__ void __launch_bounds__(128) k_reduce_level0(ReduceArgs a) {
   reduce_level0_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-__global__ void __launch_bounds__(128) k_reduce_level(ReduceArgs a) {
-  reduce_level_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(256) k_reduce_block(BlockLevelArgs a) {
+  __shared__ G1XYZZ sh[256];
+  const uint32_t t = threadIdx.x, chunk = blockIdx.x, set = blockIdx.y;
+  G1XYZZ s, x;
+  blk_local(a, set, chunk, t, s, x);
+  sh[t] = s;
+  __syncthreads();
+  for (uint32_t d = 1; d < 256; d <<= 1) {
+    const G1XYZZ v = blk_scan_step(sh, t, d);
+    __syncthreads();
+    sh[t] = v;
+    __syncthreads();
+  }
+  const G1XYZZ suf = sh[t];  // thread 0 keeps S' = suf_0
+  const G1XYZZ y = blk_weight(a, t, x, suf);
+  __syncthreads();
+  sh[t] = y;
+  __syncthreads();
+  for (uint32_t d = 128; d > 0; d >>= 1) {
+    blk_tree_step(sh, t, d);
+    __syncthreads();
+  }
+  if (t == 0) {
+    SR o;
+    o.S = suf;
+    o.R = sh[0];
+    a.out[(uint64_t)set * gridDim.x + chunk] = o;
+  }
 }
 
 // affine points: canonical <-> Montgomery (both coordinates)
@@ -419,24 +446,50 @@ static uint32_t env_u32(const char* name, uint32_t dflt) {
   return e ? (uint32_t)atoi(e) : dflt;
 }
 
-// additions per thread of an accumulation round over `items` candidate additions: as many as BMAX while the launch
-// still fills the machine a few times over (a thread's inversion is amortised over its additions)
-static uint32_t pick_B(Context* ctx, uint64_t items) {
+// Chain length of an accumulation round (see AffAcc::B): as long as the launch still fills the machine.  A
+// thread's safegcd inversion costs about as much as 8 additions, so short chains are expensive; the integer pipe is
+// saturated by two resident warps per scheduler, so 256 threads per SM is "full".
+static uint32_t pick_B(Context* ctx, uint64_t slots, uint32_t r) {
   static const uint32_t forced = env_u32("PB200_MSM_B", 0);
-  if (forced) return std::min<uint32_t>(std::max<uint32_t>(forced, 1), PB_AFF_BMAX);
-  const uint64_t resident = (uint64_t)ctx->sm_count * 512;
-  for (uint32_t B : {64u, 48u, 32u, 24u}) if (items / B >= 3 * resident) return B;
+  const uint32_t cap = r == 0 ? 64 : PB_AFF_BMAX;  // round 0 is dense: B additions; later rounds: about B / 2
+  if (forced) return std::min<uint32_t>(std::max<uint32_t>(r == 0 ? forced : 2 * forced, 2), cap);
+  const uint64_t full = (uint64_t)ctx->sm_count * 256;
+  for (uint32_t B = cap; B > 16; B >>= 1)
+    if (slots / aff_round_span(B, r) >= 2 * full) return B;
   return 16;
+}
+
+// sum over ranks rho of (R_rho + rho * nloc * S_rho) for every bucket set: the partial sums of equal bucket ranges
+// [rho * nloc, (rho + 1) * nloc), nloc a power of two.  all: [world][sets] (S, R) pairs.
+void host_join_bucket_shards(const SR* all, uint32_t world, uint32_t sets, uint32_t nloc, G1XYZZ* out) {
+  uint32_t log_nloc = 0;
+  while ((1u << log_nloc) < nloc) log_nloc++;
+  PB_CHECK((1u << log_nloc) == nloc, "bucket shards must be a power of two wide");
+  for (uint32_t s = 0; s < sets; s++) {
+    G1XYZZ run = G1XYZZ::identity(), weighted = G1XYZZ::identity(), plain = G1XYZZ::identity();
+    for (uint32_t rho = world; rho-- > 0;) {
+      const SR& e = all[(size_t)rho * sets + s];
+      g1_add(plain, e.R);
+      if (rho >= 1) {
+        g1_add(run, e.S);       // sum_{rho' >= rho} S
+        g1_add(weighted, run);  // -> sum rho * S_rho
+      }
+    }
+    for (uint32_t k = 0; k < log_nloc; k++) g1_double(weighted);
+    g1_add(plain, weighted);
+    out[s] = plain;
+  }
 }
 
 // points: Montgomery affine (generic: n points; fixed-base: expanded table W*n).
 // batch > 1 (fixed-base only): `batch` scalar vectors against the same points in one pass; the k-th MSM uses bucket
 // set k.  [bucket_lo, bucket_hi): the bucket magnitudes this call owns (0, 2^(c-1) = everything); with a proper
-// sub-range the result is this rank's partial sum.
+// sub-range the result is this rank's partial sum.  comm != nullptr: the ranks of the communicator split the buckets
+// evenly, exchange their 256-byte (S, R) pairs with one allgather and all return the full result.
 void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* const* scalars, uint32_t batch,
                    bool scalars_mont, uint32_t c, bool fixed_base, uint64_t point_stride, uint32_t bucket_lo,
                    uint32_t bucket_hi, uint8_t* out_xy /*batch*64*/, int* is_identity /*batch*/,
-                   G1XYZZ* raw_out /*optional: batch XYZZ sums instead of affine*/) {
+                   G1XYZZ* raw_out /*optional: batch XYZZ sums instead of affine*/, Comm* comm = nullptr) {
   PB_CHECK(n > 0, "empty MSM");
   PB_CHECK(batch >= 1 && batch <= 4 && (fixed_base || batch == 1), "bad MSM batch");
   MsmGeom g;
@@ -446,6 +499,14 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   g.fixed_base = fixed_base ? 1 : 0;
   g.point_stride = fixed_base ? point_stride : 0;
   g.batch = batch;
+  if (comm && comm_world(comm) > 1) {
+    const uint32_t per = g.half >> comm_log_world(comm);
+    PB_CHECK(per >= 1, "more ranks than buckets");
+    bucket_lo = per * (uint32_t)comm_rank(comm);
+    bucket_hi = bucket_lo + per;
+  } else {
+    comm = nullptr;
+  }
   if (bucket_hi > g.half) bucket_hi = g.half;
   PB_CHECK(bucket_lo < bucket_hi, "empty MSM bucket range");
   g.lo = bucket_lo;
@@ -456,7 +517,9 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   ScalarBatch sb;
   for (uint32_t k = 0; k < 4; k++) sb.p[k] = k < batch ? scalars[k] : nullptr;
 
-  static const bool use_xyzz = [] { const char* e = getenv("PB200_MSM_ACC"); return e && !strcmp(e, "xyzz"); }();
+  // XYZZ segment accumulation is the default: measured on B200 (profiles/r02_msm_affine_vs_xyzz.md) the batched-affine
+  // rounds spend in field additions and the safegcd inversion (ALU pipe) what they save in multiplications
+  static const bool use_xyzz = [] { const char* e = getenv("PB200_MSM_ACC"); return !(e && !strcmp(e, "affine")); }();
   const uint32_t pad = use_xyzz ? 0 : 1;
   DevBuf& sorted = ctx->scratch[2];
   DevBuf& counts = ctx->scratch[3];
@@ -511,14 +574,14 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     ctx->time_begin(0);
     for (uint32_t r = 0; r < std::min<uint32_t>(max_rounds, PB_AFF_GRID_ROUNDS); r++) {
       a.r = r;
-      a.B = pick_B(ctx, s_bound >> r);
+      a.B = pick_B(ctx, s_bound, r);
       const uint64_t threads = aff_round_threads(s_bound, a.B, r);
       if (r == 0) k_aff_round0<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
       else k_aff_round<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
       ctx->launches++;
     }
     if (max_rounds > PB_AFF_GRID_ROUNDS) {
-      a.B = 16;
+      a.B = 32;
       k_aff_tail<<<1, 256, 0, st>>>(a, s_bound);
       ctx->launches++;
     }
@@ -561,8 +624,6 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   ra.sets = g.sets;
   ra.m = g.nloc;
   ra.g = 1u << log_g0;
-  ra.log_G = 0;
-  ra.in = nullptr;
   {
     const uint64_t groups = (uint64_t)g.sets * reduce_groups(ra.m, ra.g);
     lvl_a.ensure(groups * sizeof(SR));
@@ -574,32 +635,42 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   uint32_t m = reduce_groups(ra.m, ra.g), log_G = log_g0;
   SR* cur = lvl_a.as<SR>();
   SR* nxt = lvl_b.as<SR>();
-  ra.pts = nullptr; ra.xb = nullptr;
   while (m > 1) {
-    ra.in = cur;
-    ra.out = nxt;
-    ra.m = m;
-    ra.g = 16;
-    ra.log_G = log_G;
-    const uint64_t groups = (uint64_t)g.sets * reduce_groups(m, 16);
-    k_reduce_level<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(ra);
+    BlockLevelArgs ba;
+    ba.in = cur; ba.out = nxt; ba.sets = g.sets; ba.m = m; ba.log_G = log_G;
+    k_reduce_block<<<dim3(reduce_chunks(m), g.sets), 256, 0, st>>>(ba);
     ctx->launches++;
-    m = reduce_groups(m, 16);
-    log_G += 4;
+    m = reduce_chunks(m);
+    log_G += 10;
     std::swap(cur, nxt);
   }
   ctx->time_end(3);
   PB_CUDA(cudaGetLastError());
-  std::vector<SR> fin(g.sets);
-  PB_CUDA(cudaMemcpyAsync(fin.data(), cur, g.sets * sizeof(SR), cudaMemcpyDeviceToHost, st));
-  PB_CUDA(cudaStreamSynchronize(st));
-  // set result = sum_j (lo + j + 1) B_j = R + lo * S
   std::vector<G1XYZZ> ws(g.sets);
-  for (uint32_t s = 0; s < g.sets; s++) {
-    ws[s] = fin[s].R;
-    if (g.lo) {
-      G1XYZZ m_lo = host_mul_small(fin[s].S, g.lo);
-      g1_add(ws[s], m_lo);
+  if (comm) {
+    // the MSM join: one allgather of sets * 256 bytes per rank, then a few host additions (the commitment has to
+    // reach the host for the Fiat-Shamir transcript anyway)
+    const uint32_t world = (uint32_t)comm_world(comm);
+    DevBuf& gath = ctx->msm_aff[2];
+    gath.ensure((size_t)world * g.sets * sizeof(SR));
+    SR* all = gath.as<SR>();
+    PB_CUDA(cudaMemcpyAsync(all + (size_t)comm_rank(comm) * g.sets, cur, g.sets * sizeof(SR), cudaMemcpyDeviceToDevice, st));
+    comm_allgather_inplace(comm, all, g.sets * sizeof(SR), st);
+    std::vector<SR> fin((size_t)world * g.sets);
+    PB_CUDA(cudaMemcpyAsync(fin.data(), all, fin.size() * sizeof(SR), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    host_join_bucket_shards(fin.data(), world, g.sets, g.nloc, ws.data());
+  } else {
+    std::vector<SR> fin(g.sets);
+    PB_CUDA(cudaMemcpyAsync(fin.data(), cur, g.sets * sizeof(SR), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    // set result = sum_j (lo + j + 1) B_j = R + lo * S
+    for (uint32_t s = 0; s < g.sets; s++) {
+      ws[s] = fin[s].R;
+      if (g.lo) {
+        G1XYZZ m_lo = host_mul_small(fin[s].S, g.lo);
+        g1_add(ws[s], m_lo);
+      }
     }
   }
   if (raw_out) {
@@ -804,6 +875,18 @@ void srs_msm_batch_partial(Context* ctx, Srs* srs, const Fr* const* d_scalars, u
                 bucket_lo, bucket_hi, nullptr, nullptr, out);
 }
 uint32_t srs_bucket_count(Srs* s) { return s->c ? 1u << (s->c - 1) : 0; }
+
+// `batch` commitments with the buckets split over the ranks of the context's communicator (every rank holds the
+// full scalar vectors and an SRS replica): one allgather of 256 bytes per commitment and rank at the join, the same
+// affine results on every rank.
+void srs_msm_batch_sharded(Context* ctx, Srs* srs, const Fr* const* d_scalars, uint32_t batch, uint64_t m,
+                           bool scalars_mont, uint8_t* out_xy, int* is_identity) {
+  PB_CHECK(m <= srs->n, "Not enough powers in setup");
+  PB_CHECK(srs->expanded.p, "sharded commitments need the fixed-base table (precompute)");
+  PB_CHECK(ctx->comm, "sharded commitments need a communicator on the context (pb200_comm_init)");
+  msm_run_batch(ctx, srs->expanded.as<G1Affine>(), m, d_scalars, batch, scalars_mont, srs->c, true, srs->n, 0,
+                0xffffffffu, out_xy, is_identity, nullptr, ctx->comm);
+}
 
 // sum of XYZZ partials -> canonical affine (host arithmetic; O(count) group operations)
 void g1_combine_partials_host(const G1XYZZ* parts, uint32_t count, uint8_t* out_xy, int* is_identity) {

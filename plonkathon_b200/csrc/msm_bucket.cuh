@@ -22,16 +22,20 @@
 // denominator 2y), opposite points give the identity (encoded x.v[7] == 0xffffffff, not a reduced element), an
 // identity operand returns the other one.
 //
-// Reduction = sum_j (j+1) B_j by recursive grouped running sums: level 0 turns g consecutive buckets into
-// (S, R) = (sum B, sum (lo+1) B); with F = G sum_i i S_i + sum_i R_i as the invariant (G = g^level), a level folds
-// g elements into S' = sum S, R' = G sum_lo lo S_lo + sum R.  Every level is one thread per group, so the bottom
-// level -- all the work -- runs at full width; the sequential depth is g additions per level.
+// Reduction = sum_j (j+1) B_j by recursive grouping: level 0 turns g consecutive buckets into
+// (S, R) = (sum B, sum (lo+1) B) with one thread per group (running sums, all the work, full width); with
+// F = G sum_i i S_i + sum_i R_i as the invariant (G = product of the group sizes below), a higher level folds 1024
+// elements into S' = sum S, R' = G sum_lo lo S_lo + sum R with one block per group (suffix scan + tree).
 //
 // The bodies are host/device functions so tests/test_host_arith.py can run the whole pipeline on the CPU
 // (csrc/host_selftest.cpp) against the oracle's group law; the __global__ wrappers live in msm.cu.
 #pragma once
 #include "curve.cuh"
 #include "modinv.cuh"
+#if !defined(__CUDA_ARCH__)
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 namespace pb200 {
 
@@ -39,7 +43,7 @@ namespace pb200 {
 #define PB_AFF_DBL 2u
 #define PB_AFF_INDEX_BITS 29
 #define PB_AFF_INDEX_MASK ((1u << PB_AFF_INDEX_BITS) - 1)
-#define PB_AFF_BMAX 64          // additions per thread and inversion (upper bound; the launch picks B <= BMAX)
+#define PB_AFF_BMAX 128         // capacity of a thread's chain of additions (one inversion per chain)
 #define PB_MSM_PAD 0xffffffffu  // `sorted` filler of padding positions
 #define PB_AFF_GRID_ROUNDS 12   // rounds launched grid-wide (buckets up to 4096 entries); the rest: one-block tail
 
@@ -52,7 +56,9 @@ struct AffAcc {
   const uint32_t* max_cnt;  // largest bucket size (device scalar)
   uint32_t nbl;             // buckets of this launch (all bucket sets)
   uint32_t r;               // round
-  uint32_t B;               // additions per thread
+  uint32_t B;               // round 0: slots (= additions) per thread; round r >= 1: a thread's range is B * 2^(r-1)
+                            // slots, which holds at most B additions (left-hand slots are more than 2^(r-1) apart)
+                            // and about B / 2 when the buckets are large.  B <= PB_AFF_BMAX.
 };
 
 PB_HD bool aff_is_identity_x(const Fq& x) { return x.v[7] == 0xffffffffu; }
@@ -138,9 +144,11 @@ PB_HD uint32_t aff_classify_equal_x(const Fq& y1, const Fq& y2, Fq& d) {
   return 0;
 }
 
+// slots per thread in round r
+PB_HD uint64_t aff_round_span(uint32_t B, uint32_t r) { return r == 0 ? B : (uint64_t)B << (r - 1); }
 // threads a grid-wide launch of round r needs for S_bound slots
 PB_HD uint64_t aff_round_threads(uint64_t s_bound, uint32_t B, uint32_t r) {
-  const uint64_t per = (uint64_t)B << r;
+  const uint64_t per = aff_round_span(B, r);
   uint64_t t = (s_bound + per - 1) / per;
   return r == 0 ? ((t + 31) / 32) * 32 : t;  // round 0 hands whole warps 32 * B slots
 }
@@ -198,10 +206,11 @@ PB_HD void aff_round_thread(const AffAcc& a, uint64_t t, Fq* pref, uint32_t* des
   if (r >= 32 || aff_ld_u32(a.max_cnt) <= (1u << r)) return;  // every bucket has m0 <= 2^(r-1): nothing to pair
   const uint32_t S = aff_ld_u32(a.off + a.nbl) >> 1;
   const uint64_t step = 1ull << r, hs = step >> 1;
-  const uint64_t lo64 = t * a.B * step;
+  const uint64_t span = a.B * hs;  // two left-hand slots are at least hs + 1 apart: at most B of them in the range
+  const uint64_t lo64 = t * span;
   if (lo64 >= S) return;
   const uint32_t lo = (uint32_t)lo64;
-  const uint32_t hi = (uint32_t)(lo64 + a.B * step < S ? lo64 + a.B * step : S);
+  const uint32_t hi = (uint32_t)(lo64 + span < S ? lo64 + span : S);
   uint32_t b = aff_upper_bound(a.off, 0, a.nbl + 1, 2 * lo) - 1;  // off[b] <= 2 lo < off[b+1]
   Fq acc = Fq::one();
   uint32_t K = 0;
@@ -231,6 +240,9 @@ PB_HD void aff_round_thread(const AffAcc& a, uint64_t t, Fq* pref, uint32_t* des
           continue;
         }
       }
+#if !defined(__CUDA_ARCH__)
+      if (K >= a.B) { fprintf(stderr, "aff_round_thread: chain longer than B\n"); abort(); }  // host self-test only
+#endif
       pref[K] = acc;
       desc[K] = left | (kind << PB_AFF_INDEX_BITS);
       K++;
@@ -292,13 +304,10 @@ struct ReduceArgs {
   const uint32_t* off;
   const uint32_t* cnt;
   const G1XYZZ* xb;   // alternative level 0 input: one XYZZ point per bucket (nullptr: use pts / off / cnt)
-  // level >= 1 input
-  const SR* in;
   SR* out;
   uint32_t sets;      // bucket sets (windows / batched commitments)
-  uint32_t m;         // elements per set at this level's input
+  uint32_t m;         // buckets per set
   uint32_t g;         // group size
-  uint32_t log_G;     // log2 of G = product of the group sizes of the levels below (doublings applied to wsum)
 };
 PB_HD uint32_t reduce_groups(uint32_t m, uint32_t g) { return (m + g - 1) / g; }
 
@@ -341,27 +350,63 @@ PB_HD void reduce_level0_thread(const ReduceArgs& a, uint64_t t) {
   a.out[t] = o;
 }
 
-// level >= 1, thread t = set * groups + hi: S' = sum S, R' = G * sum_lo lo S_lo + sum R
-PB_HD void reduce_level_thread(const ReduceArgs& a, uint64_t t) {
-  const uint32_t groups = reduce_groups(a.m, a.g);
-  if (t >= (uint64_t)a.sets * groups) return;
-  const uint32_t set = (uint32_t)(t / groups), hi = (uint32_t)(t % groups);
-  const uint32_t j0 = hi * a.g;
-  const uint32_t len = a.m - j0 < a.g ? a.m - j0 : a.g;
-  const SR* base = a.in + (uint64_t)set * a.m + j0;
-  G1XYZZ acc = G1XYZZ::identity(), wsum = G1XYZZ::identity(), rsum = G1XYZZ::identity();
-  for (uint32_t k = len; k-- > 0;) {
-    const SR e = base[k];
-    g1_add_uniform(acc, e.S);
-    if (k >= 1) g1_add_uniform(wsum, acc);  // sum_{lo >= 1} sum_{lo' >= lo} S_lo' = sum lo S_lo
-    g1_add_uniform(rsum, e.R);
+// ---- levels >= 1: one block of 256 threads folds a chunk of 1024 elements ------------------------------------
+// Above level 0 there are too few elements to fill the machine, so a level is bound by the length of its chains of
+// dependent additions, not by throughput: a block-wide suffix scan and a tree keep that length at ~25 additions for
+// a group of 1024 (a thread-per-group level of 16 has 48, and four times as many levels).
+//   element index in the chunk: lo = 4 t + e, e < 4;   S' = sum S,   R' = G sum_lo lo S_lo + sum R
+//   thread t: s_t = sum_e S, w_t = sum_e e S_e, r_t = sum_e R  ->  x_t = r_t + G w_t
+//   suffix scan: suf_t = sum_{t' >= t} s_t'                     ->  S' = suf_0, sum_t t s_t = sum_{t >= 1} suf_t
+//   y_t = x_t + 4 G suf_t (t >= 1), tree sum of y               ->  R'
+#define PB_REDUCE_CHUNK 1024
+struct BlockLevelArgs {
+  const SR* in;
+  SR* out;
+  uint32_t sets, m;   // input elements per set
+  uint32_t log_G;     // log2 of the weight G of this level's element index
+};
+PB_HD uint32_t reduce_chunks(uint32_t m) { return (m + PB_REDUCE_CHUNK - 1) / PB_REDUCE_CHUNK; }
+
+PB_HD void blk_local(const BlockLevelArgs& a, uint32_t set, uint32_t chunk, uint32_t t, G1XYZZ& s, G1XYZZ& x) {
+  const uint64_t i0 = (uint64_t)chunk * PB_REDUCE_CHUNK + 4 * t;
+  const SR* base = a.in + (uint64_t)set * a.m;
+  G1XYZZ acc = G1XYZZ::identity(), w = G1XYZZ::identity(), r = G1XYZZ::identity();
+  for (int e = 3; e >= 0; e--) {
+    if (i0 + e >= a.m) continue;
+    const SR v = base[i0 + e];
+    g1_add(acc, v.S);
+    if (e >= 1) g1_add(w, acc);
+    g1_add(r, v.R);
   }
-  for (uint32_t d = 0; d < a.log_G; d++) g1_double(wsum);
-  g1_add(rsum, wsum);
-  SR o;
-  o.S = acc;
-  o.R = rsum;
-  a.out[t] = o;
+  for (uint32_t d = 0; d < a.log_G; d++) g1_double(w);
+  g1_add(r, w);
+  s = acc;
+  x = r;
+}
+// one Hillis-Steele step of the inclusive suffix scan: value of position t after combining with t + d
+PB_HD G1XYZZ blk_scan_step(const G1XYZZ* sh, uint32_t t, uint32_t d) {
+  G1XYZZ v = sh[t];
+  if (t + d < 256) {
+    const G1XYZZ o = sh[t + d];
+    g1_add(v, o);
+  }
+  return v;
+}
+PB_HD G1XYZZ blk_weight(const BlockLevelArgs& a, uint32_t t, const G1XYZZ& x, G1XYZZ suf) {
+  G1XYZZ y = x;
+  if (t >= 1) {
+    for (uint32_t d = 0; d < a.log_G + 2; d++) g1_double(suf);
+    g1_add(y, suf);
+  }
+  return y;
+}
+PB_HD void blk_tree_step(G1XYZZ* sh, uint32_t t, uint32_t d) {
+  if (t < d) {
+    G1XYZZ u = sh[t];
+    const G1XYZZ v = sh[t + d];
+    g1_add(u, v);
+    sh[t] = u;
+  }
 }
 
 }  // namespace pb200

@@ -16,6 +16,8 @@
 // writes transposed, CC x 32 B contiguous per row.  The per-pass local twiddles w_B^j are staged into shared
 // memory with one TMA bulk copy (cp.async.bulk + mbarrier).
 #include "common.cuh"
+#include "comm.cuh"
+#include "ntt_shard.cuh"
 
 namespace pb200 {
 
@@ -100,7 +102,9 @@ struct PassParams {
   const Fr* out_scale;  // optional multiply-on-store table, indexed by global output index
   uint64_t n_in;        // input indices >= n_in read as zero
   uint64_t in_mul, in_add;  // physical input index = logical * in_mul + in_add (strided sub-sequence, first pass)
-  uint32_t log_b, log_cc, t_lo_count, b_fastest_load, has_final_scale;
+  uint32_t fold;            // first pass: logical input i is sum_f (in * in_scale)[i + f * 2^log_n], f < fold (a
+                            // polynomial longer than the transform, reduced mod X^N - c^N on the fly)
+  uint32_t log_b, log_cc, t_lo_count, b_fastest_load, has_final_scale, log_n;
   uint64_t r_hi, r_lo, r_cs, r_bs;
   uint64_t w_hi, w_lo, w_cs, w_bs;
   uint64_t g_hi, g_lo, g_cs, g_bs;
@@ -236,6 +240,14 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
     if (gi < p.n_in) {
       x = ld_global(p.in + gi * p.in_mul + p.in_add);
       if (p.in_scale) x = fp_mul(x, ld_global(p.in_scale + gi));
+    }
+    for (uint32_t f = 1; f < p.fold; f++) {
+      const uint64_t gf = gi + ((uint64_t)f << p.log_n);
+      if (gf < p.n_in) {
+        Fr y = ld_global(p.in + gf * p.in_mul + p.in_add);
+        if (p.in_scale) y = fp_mul(y, ld_global(p.in_scale + gf));
+        x = fp_add(x, y);
+      }
     }
     uint32_t br = p.log_b ? (__brev(b) >> (32 - p.log_b)) : 0;
     st_planes(s_lo, s_hi, (br << p.log_cc) | c, x);
@@ -416,6 +428,8 @@ static std::unique_ptr<NttPlan> build_plan(Context* ctx, int log_n, bool inverse
     }
     (void)batch;
     q.log_cc = ps.log_cc;
+    q.log_n = log_n;
+    q.fold = 1;
     ps.tiles = N >> (lb[i] + ps.log_cc);
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
     PB_CHECK(smem <= 227 * 1024, "NTT tile does not fit shared memory");
@@ -428,11 +442,8 @@ NttPlan* get_plan(Context* ctx, int log_n, bool inverse) {
   int key = log_n * 2 + (inverse ? 1 : 0);
   auto it = ctx->plans.find(key);
   if (it != ctx->plans.end()) return it->second.get();
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (ctx->plans.empty())  // once per context, i.e. on this context's device (the attribute is per device)
     PB_CUDA(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   auto plan = build_plan(ctx, log_n, inverse);
   NttPlan* raw = plan.get();
   ctx->plans[key] = std::move(plan);
@@ -443,6 +454,8 @@ Context::Context() {}
 
 Context::~Context() {
   plans.clear();
+  shard_tables.clear();
+  if (comm) comm_destroy(comm);
   for (auto& e : copy_done) if (e) cudaEventDestroy(e);
   for (auto& e : aux_ev) if (e) cudaEventDestroy(e);
   if (aux_stream) cudaStreamDestroy(aux_stream);
@@ -464,6 +477,8 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
 
 void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
                 uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
+void ntt_run_fold(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
+                  uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add, uint32_t fold);
 
 void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint64_t n_in,
                      const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add) {
@@ -474,6 +489,13 @@ void ntt_run_strided(Context* ctx, const Fr* in, Fr* out, int log_n, bool invers
 // transform can overlap work on the context's main stream; tmp == nullptr uses the context's scratch.
 void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
                 uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add) {
+  ntt_run_fold(ctx, stream, tmp, in, out, log_n, inverse, n_in, in_scale, out_scale, in_mul, in_add, 1);
+}
+
+// fold > 1: the logical input has fold * 2^log_n entries (of which n_in are non-zero) and is wrapped around the
+// transform length on load -- evaluating a polynomial of degree >= 2^log_n on a 2^log_n-point (coset) domain.
+void ntt_run_fold(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
+                  uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add, uint32_t fold) {
   NttPlan* plan = get_plan(ctx, log_n, inverse);
   const uint64_t N = (uint64_t)1 << log_n;
   int np = (int)plan->passes.size();
@@ -493,6 +515,7 @@ void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* ou
     q.in_add = (i == 0) ? in_add : 0;
     q.in_scale = (i == 0) ? in_scale : nullptr;
     q.out_scale = (i == np - 1) ? out_scale : nullptr;
+    q.fold = (i == 0) ? fold : 1;
     size_t smem = pass_smem_bytes(ps.log_b, ps.log_cc);
     if (main_stream) ctx->time_begin(1);
     k_ntt_pass<<<(unsigned)ps.tiles, PB_NTT_THREADS, smem, stream>>>(q);
@@ -502,36 +525,114 @@ void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* ou
   PB_CUDA(cudaGetLastError());
 }
 
-// ---- multi-GPU slab NTT: the join after the allgather ------------------------------------------------
-// N = G * M.  Rank h transformed the decimated sequence x[h::G] into Y_h (size M).  With all G sub-spectra
-// gathered (sub = [G][M]), the contiguous output slab s is X[s*M + t] = sum_h w_N^(h (s M + t)) Y_h[t]: a
-// length-G DFT per element, evaluated by Horner in w_N^k (G - 1 products; G <= 8 in one box).
-__global__ void __launch_bounds__(128) k_ntt_slab_combine(const Fr* sub, Fr* out, uint64_t M, uint32_t G, uint64_t slab,
-                                                          Fr wN, Fr scale) {
-  const int CH = 16;
-  uint64_t t0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * CH;
-  if (t0 >= M) return;
-  Fr w = fp_pow_u64(wN, slab * M + t0);
-  for (int j = 0; j < CH && t0 + j < M; j++) {
-    uint64_t t = t0 + j;
-    Fr acc = ld_global(sub + (uint64_t)(G - 1) * M + t);
-    for (int h = (int)G - 2; h >= 0; h--) acc = fp_add(fp_mul(acc, w), ld_global(sub + (uint64_t)h * M + t));
-    st_global(out + t, fp_mul(acc, scale));
-    w = fp_mul(w, wN);
+// ---- multi-GPU slab NTT (ntt_shard.cuh) -----------------------------------------------------------------------
+struct ShardTables {
+  DevBuf store_tw;  // w_N^(+-r k0) (* 1/G for the inverse), k0 < M: the local transform's multiply-on-store table
+  DftTw dft;        // w_G^(+-k), k < G/2
+};
+
+struct CombineArgs {
+  const Fr* sub;         // gathered sub-spectra: rank r's vector at sub + r * rank_stride
+  Fr* out;
+  uint64_t M, rank_stride;
+  uint64_t limit;        // outputs with index >= limit are not stored; they must be zero (counted in *nonzero)
+  const Fr* post_scale;  // optional per-output multiplier (indexed like out)
+  uint32_t* nonzero;
+  DftTw tw;
+};
+template <int LG>
+__global__ void __launch_bounds__(128) k_shard_combine(CombineArgs a) {
+  constexpr int G = 1 << LG;
+  const uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k0 >= a.M) return;
+  Fr x[G];
+#pragma unroll
+  for (int r = 0; r < G; r++) x[r] = ld_global(a.sub + (uint64_t)r * a.rank_stride + k0);
+  small_dft<LG>(x, a.tw);
+#pragma unroll
+  for (int k1 = 0; k1 < G; k1++) {
+    const uint64_t k = k0 + (uint64_t)k1 * a.M;
+    if (k < a.limit) {
+      Fr v = x[k1];
+      if (a.post_scale) v = fp_mul(v, ld_global(a.post_scale + k));
+      st_global(a.out + k, v);
+    } else if (!x[k1].is_zero()) {
+      atomicAdd(a.nonzero, 1u);
+    }
   }
 }
 
-// inverse: the sub-transforms already carry 1/M, the join adds 1/G
-void ntt_slab_combine(Context* ctx, const Fr* sub, Fr* out, int log_m, int log_g, uint64_t slab, bool inverse) {
-  uint64_t M = (uint64_t)1 << log_m;
-  uint32_t G = 1u << log_g;
-  Fr wN = fr_root_of_unity(log_m + log_g);
-  Fr scale = Fr::one();
-  if (inverse) { wN = fp_inv(wN); scale = fp_inv(fr_from_u64(G)); }
-  uint64_t threads = (M + 15) / 16;
-  k_ntt_slab_combine<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(sub, out, M, G, slab, wN, scale);
+Comm* ctx_comm(Context* ctx);
+
+static ShardTables* get_shard_tables(Context* ctx, int log_n, bool inverse) {
+  Comm* cm = ctx_comm(ctx);
+  const int key = log_n * 2 + (inverse ? 1 : 0);
+  auto it = ctx->shard_tables.find(key);
+  if (it != ctx->shard_tables.end()) return it->second.get();
+  const int log_g = comm_log_world(cm), rank = comm_rank(cm);
+  PB_CHECK(log_n > log_g, "sharded transform: fewer points than ranks");
+  const uint64_t M = (uint64_t)1 << (log_n - log_g);
+  auto t = std::make_unique<ShardTables>();
+  Fr w = fr_root_of_unity(log_n);
+  if (inverse) w = fp_inv(w);
+  Fr scale = inverse ? fp_inv(fr_from_u64((uint64_t)1 << log_g)) : Fr::one();
+  t->store_tw.alloc(M * 32);
+  launch_powers(ctx, t->store_tw.as<Fr>(), M, fp_pow_u64(w, (uint64_t)rank), scale);
+  Fr wg = fp_pow_u64(w, M), cur = Fr::one();
+  for (int k = 0; k < 4; k++) { t->dft.w[k] = cur; cur = fp_mul(cur, wg); }
+  ShardTables* raw = t.get();
+  ctx->shard_tables[key] = std::move(t);
+  return raw;
+}
+
+// the join: ctx->gather holds the G sub-spectra (rank r at r * rank_stride elements, M valid entries each)
+void ntt_shard_combine(Context* ctx, const Fr* sub, uint64_t rank_stride, Fr* out, int log_n, bool inverse,
+                       uint64_t limit, const Fr* post_scale, uint32_t* nonzero) {
+  Comm* cm = ctx_comm(ctx);
+  const int log_g = comm_log_world(cm);
+  ShardTables* t = get_shard_tables(ctx, log_n, inverse);
+  CombineArgs a;
+  a.sub = sub; a.out = out; a.M = (uint64_t)1 << (log_n - log_g); a.rank_stride = rank_stride;
+  a.limit = limit; a.post_scale = post_scale; a.nonzero = nonzero; a.tw = t->dft;
+  const unsigned blocks = (unsigned)((a.M + 127) / 128);
+  switch (log_g) {
+    case 1: k_shard_combine<1><<<blocks, 128, 0, ctx->stream>>>(a); break;
+    case 2: k_shard_combine<2><<<blocks, 128, 0, ctx->stream>>>(a); break;
+    case 3: k_shard_combine<3><<<blocks, 128, 0, ctx->stream>>>(a); break;
+    default: PB_CHECK(false, "sharded transform: 2, 4 or 8 ranks");
+  }
   ctx->launches++;
   PB_CUDA(cudaGetLastError());
+}
+
+// This rank's share of `count` transforms of the same size whose inputs are spread over the G ranks by decimation
+// (logical input index i of rank r = global index G i + r; physical address in[v] + i * in_mul + in_add): local
+// M-point transforms with the join twiddle fused into the store, written to the rank's place in ctx->gather
+// ([G][count][M] layout), then ONE allgather.  ntt_shard_combine finishes each vector.
+void ntt_shard_local(Context* ctx, const Fr* const* in, int count, int log_n, bool inverse, uint64_t in_mul,
+                     uint64_t in_add) {
+  Comm* cm = ctx_comm(ctx);
+  const int log_g = comm_log_world(cm), rank = comm_rank(cm), G = 1 << log_g;
+  ShardTables* t = get_shard_tables(ctx, log_n, inverse);
+  const uint64_t M = (uint64_t)1 << (log_n - log_g);
+  ctx->gather.ensure((size_t)G * count * M * 32);
+  Fr* mine = ctx->gather.as<Fr>() + (uint64_t)rank * count * M;
+  for (int v = 0; v < count; v++)
+    ntt_run_fold(ctx, ctx->stream, nullptr, in[v], mine + (uint64_t)v * M, log_n - log_g, inverse, M, nullptr,
+                 t->store_tw.as<Fr>(), in_mul, in_add, 1);
+  comm_allgather_inplace(cm, ctx->gather.p, (size_t)count * M * 32, ctx->stream);
+}
+
+// full vector in (present on every rank) -> full vector out (on every rank): poly.py:113-149 across the ranks of the
+// context's communicator with a single allgather at the join
+void ntt_sharded(Context* ctx, const Fr* const* in, Fr* const* out, int count, int log_n, bool inverse) {
+  Comm* cm = ctx_comm(ctx);
+  const int log_g = comm_log_world(cm), rank = comm_rank(cm), G = 1 << log_g;
+  const uint64_t M = (uint64_t)1 << (log_n - log_g);
+  ntt_shard_local(ctx, in, count, log_n, inverse, (uint64_t)G, (uint64_t)rank);
+  for (int v = 0; v < count; v++)
+    ntt_shard_combine(ctx, ctx->gather.as<Fr>() + (uint64_t)v * M, (uint64_t)count * M, out[v], log_n, inverse,
+                      (uint64_t)1 << log_n, nullptr, nullptr);
 }
 
 }  // namespace pb200

@@ -27,6 +27,73 @@ void fr_from_mont(Context* ctx, const Fr* in, Fr* out, uint64_t n) {
   PB_CUDA(cudaGetLastError());
 }
 
+// ---- element-wise ring operations on canonical vectors (poly.py:23-109) -------------------------------------------
+// Polynomial.__add__ / __sub__ / __mul__ / __truediv__ with a Polynomial or a Scalar operand, and Polynomial.shift,
+// for device-resident operands.  Canonical in, canonical out: a * b = mont_mul(mont_mul(a, b), R^2); a scalar operand
+// arrives in Montgomery form so one product suffices; x / y uses py_ecc's convention inv(0) == 0 (FQ.__truediv__),
+// with one safegcd inversion shared by 8 divisions (Montgomery's trick over the strided set {t, t+T, ...}).
+enum VecOp { VOP_ADD = 0, VOP_SUB, VOP_MUL, VOP_DIV, VOP_ADD_S, VOP_SUB_S, VOP_MUL_S, VOP_ADD_S0, VOP_SUB_S0, VOP_SHIFT };
+
+__global__ void k_vec_op(int op, const Fr* a, const Fr* b, Fr s_canon, Fr s_mont, Fr* out, uint64_t n, uint64_t shift) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = a[op == VOP_SHIFT ? (i + shift) % n : i], r;
+  switch (op) {
+    case VOP_ADD: r = fp_add(x, b[i]); break;
+    case VOP_SUB: r = fp_sub(x, b[i]); break;
+    case VOP_MUL: r = fp_mul(fp_mul(x, b[i]), Fr::r2()); break;
+    case VOP_ADD_S: r = fp_add(x, s_canon); break;
+    case VOP_SUB_S: r = fp_sub(x, s_canon); break;
+    case VOP_MUL_S: r = fp_mul(x, s_mont); break;
+    case VOP_ADD_S0: r = i == 0 ? fp_add(x, s_canon) : x; break;
+    case VOP_SUB_S0: r = i == 0 ? fp_sub(x, s_canon) : x; break;
+    default: r = x; break;  // VOP_SHIFT
+  }
+  out[i] = r;
+}
+
+__global__ void __launch_bounds__(128) k_vec_div(const Fr* a, const Fr* b, Fr* out, uint64_t n, uint64_t T) {
+  const int CH = 8;
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fr pref[CH], den[CH];
+  Fr run = Fr::one();
+  int cnt = 0;
+  for (int k = 0; k < CH; k++) {
+    uint64_t i = t + (uint64_t)k * T;
+    if (i >= n) break;
+    Fr d = fp_to_mont(b[i]);
+    if (d.is_zero()) d = Fr::one();
+    den[k] = d;
+    pref[k] = run;
+    run = fp_mul(run, d);
+    cnt++;
+  }
+  Fr inv = fp_inv_gcd(run);
+  for (int k = cnt - 1; k >= 0; k--) {
+    uint64_t i = t + (uint64_t)k * T;
+    Fr ik = fp_mul(inv, pref[k]);     // 1 / b_i, Montgomery form
+    inv = fp_mul(inv, den[k]);
+    out[i] = b[i].is_zero() ? Fr::zero() : fp_mul(a[i], ik);  // canonical * Montgomery -> canonical
+  }
+}
+
+void fr_vec_op(Context* ctx, int op, const Fr* a, const Fr* b, const Fr& scalar_canonical, Fr* out, uint64_t n,
+               uint64_t shift) {
+  if (!n) return;
+  PB_CHECK(op >= VOP_ADD && op <= VOP_SHIFT, "bad vector operation");
+  if (op == VOP_DIV) {
+    uint64_t T = (n + 7) / 8;
+    k_vec_div<<<(unsigned)((T + 127) / 128), 128, 0, ctx->stream>>>(a, b, out, n, T);
+  } else {
+    PB_CHECK(op != VOP_SHIFT || a != out, "shift cannot run in place");
+    k_vec_op<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, a, b, scalar_canonical, fp_to_mont(scalar_canonical),
+                                                                  out, n, shift);
+  }
+  ctx->launches++;
+  PB_CUDA(cudaGetLastError());
+}
+
 // ---- block-wide sum of Fr (any form; addition is form-agnostic) ------------------------------
 template <int NT>
 __device__ __forceinline__ Fr block_sum(Fr v, Fr* sh) {
@@ -61,7 +128,7 @@ __global__ void __launch_bounds__(128) k_bary_partial(const Fr* vals, uint64_t n
       run = fp_mul(run, d);
       if (k + 1 < cnt) wk = fp_mul(wk, w);
     }
-    Fr inv = fp_inv(run);
+    Fr inv = fp_inv_gcd(run);
     for (int k = cnt - 1; k >= 0; k--) {
       Fr d = fp_sub(x, wk);
       bool z = d.is_zero();

@@ -18,6 +18,7 @@
 // The reference's run-time invariants are kept as checks that fail the call: gate satisfaction
 // (prover.py:108-116), Z_n == 1 (prover.py:132), deg T < 3n (prover.py:205-208).
 #include "common.cuh"
+#include "comm.cuh"
 #include "transcript.cuh"
 #include "prover.cuh"
 
@@ -27,6 +28,29 @@ void ntt_run(Context* ctx, const Fr* in, Fr* out, int log_n, bool inverse, uint6
              const Fr* out_scale);
 void ntt_run_on(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
                 uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add);
+void ntt_run_fold(Context* ctx, cudaStream_t stream, Fr* tmp, const Fr* in, Fr* out, int log_n, bool inverse,
+                  uint64_t n_in, const Fr* in_scale, const Fr* out_scale, uint64_t in_mul, uint64_t in_add, uint32_t fold);
+void ntt_sharded(Context* ctx, const Fr* const* in, Fr* const* out, int count, int log_n, bool inverse);
+void ntt_shard_local(Context* ctx, const Fr* const* in, int count, int log_n, bool inverse, uint64_t in_mul,
+                     uint64_t in_add);
+void ntt_shard_combine(Context* ctx, const Fr* sub, uint64_t rank_stride, Fr* out, int log_n, bool inverse,
+                       uint64_t limit, const Fr* post_scale, uint32_t* nonzero);
+
+// Coefficients (n) -> evaluations on this rank's slice of the fixed coset (n_ext points): one forward transform of
+// size n_ext with the coset shift multiplied in on load, zero padding (n_ext > n) or wrap-around (n_ext < n).
+static void coset_extend(Prover* P, cudaStream_t stream, Fr* tmp, const Fr* coeff, Fr* out, const Fr* shift_pow) {
+  ntt_run_fold(P->ctx, stream, tmp, coeff, out, P->log_ext, false, P->n, shift_pow, nullptr, 1, 0, P->fold);
+}
+
+// n Lagrange values -> n coefficients for `count` vectors (poly.py:132-139): one device, or slab-sharded over the
+// ranks with one allgather for the whole group
+static void interpolate(Prover* P, const Fr* const* lag, Fr* const* coeff, int count) {
+  if (P->world > 1) {
+    ntt_sharded(P->ctx, lag, coeff, count, P->log_n, true);
+  } else {
+    for (int k = 0; k < count; k++) ntt_run(P->ctx, lag[k], coeff[k], P->log_n, true, P->n, nullptr, nullptr);
+  }
+}
 
 // Launch the coset extension (to the fixed 4n coset) of coefficient vectors [first, first+count) on the side
 // stream: it depends only on data already produced on the main stream, so it can fill the under-occupied
@@ -37,12 +61,14 @@ static void launch_coset_ext_async(Prover* P, int first, int count, int done_eve
     PB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->aux_ev) PB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  P->aux_tmp.ensure(4 * P->n * 32);
+  P->aux_tmp.ensure(P->n_ext * 32);
   PB_CUDA(cudaEventRecord(ctx->aux_ev[3], ctx->stream));          // inputs ready
   PB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[3], 0));
-  for (int k = first; k < first + count; k++)
-    ntt_run_on(ctx, ctx->aux_stream, P->aux_tmp.as<Fr>(), P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->log_n + 2, false,
-               P->n, P->gpow.as<Fr>(), nullptr, 1, 0);
+  for (int k = first; k < first + count; k++) {
+    coset_extend(P, ctx->aux_stream, P->aux_tmp.as<Fr>(), P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->gpow.as<Fr>());
+    if (k == 3 && P->zw_separate)  // Z(wX) on the slice: the same coefficients on the coset shifted by w
+      coset_extend(P, ctx->aux_stream, P->aux_tmp.as<Fr>(), P->coeff[3].as<Fr>(), P->ext[5].as<Fr>(), P->gpow_w.as<Fr>());
+  }
   PB_CUDA(cudaEventRecord(ctx->aux_ev[done_event], ctx->aux_stream));
 }
 void launch_powers(Context* ctx, Fr* out, uint64_t n, const Fr& base, const Fr& scale);
@@ -116,7 +142,7 @@ __global__ void __launch_bounds__(128) k_batch_div(const Fr* num, const Fr* den,
     run = fp_mul(run, d);
     cnt++;
   }
-  Fr inv = fp_inv(run);
+  Fr inv = fp_inv_gcd(run);
   for (int k = cnt - 1; k >= 0; k--) {
     uint64_t i = t + (uint64_t)k * T;
     Fr d = ldg_fr(den + i);
@@ -263,12 +289,14 @@ __global__ void k_lagrange_den(const Fr* X, uint64_t n4, Fr wi, Fr n_mont, Fr* d
 
 // ---- round 3: quotient on the fixed coset -----------------------------------------------------------------
 struct QuotientArgs {
-  const Fr *A, *B, *C, *Z, *PI;                       // extended (4n)
+  const Fr *A, *B, *C, *Z, *Zw, *PI;                  // extended (this rank's slice); Zw[j + zw_shift] = Z(w x_j)
   const Fr *QL, *QR, *QM, *QO, *QC, *S1, *S2, *S3;    // extended, cached per circuit
   const Fr *L0, *X;                                   // extended L0 and the coset points
   Fr zh_inv[4];                                       // 1 / (x_j^n - 1) for j mod 4
   Fr alpha, alpha2, beta, gamma, one;
-  uint64_t n4;
+  uint64_t n4;                                         // points of the slice
+  uint64_t zw_shift;
+  uint32_t world, rank;                                // global coset index of local j: world * j + rank
   // public inputs: PI(x_j) = sum_i pi_coef[i] * pi_basis[i][j]  (pi_cnt > 0), else the extended vector PI
   int pi_cnt;
   const Fr* pi_basis[8];
@@ -277,7 +305,7 @@ struct QuotientArgs {
 __global__ void __launch_bounds__(128) k_quotient(QuotientArgs q, Fr* T) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= q.n4) return;
-  uint64_t jw = j + 4 >= q.n4 ? j + 4 - q.n4 : j + 4;
+  uint64_t jw = j + q.zw_shift >= q.n4 ? j + q.zw_shift - q.n4 : j + q.zw_shift;
   Fr a = ldg_fr(q.A + j), b = ldg_fr(q.B + j), c = ldg_fr(q.C + j);
   Fr gate = fp_mul(a, ldg_fr(q.QL + j));
   gate = fp_add(gate, fp_mul(b, ldg_fr(q.QR + j)));
@@ -293,7 +321,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs q, Fr* T) {
   Fr ag = fp_add(a, q.gamma), bg = fp_add(b, q.gamma), cg = fp_add(c, q.gamma);
   Fr bx = fp_mul(q.beta, ldg_fr(q.X + j));
   Fr bx2 = fp_dbl(bx), bx3 = fp_add(bx2, bx);
-  Fr z = ldg_fr(q.Z + j), zw = ldg_fr(q.Z + jw);
+  Fr z = ldg_fr(q.Z + j), zw = ldg_fr(q.Zw + jw);
   Fr p1 = fp_mul(fp_mul(fp_mul(fp_add(ag, bx), fp_add(bg, bx2)), fp_add(cg, bx3)), z);
   Fr p2 = fp_mul(fp_mul(fp_mul(fp_add(ag, fp_mul(q.beta, ldg_fr(q.S1 + j))), fp_add(bg, fp_mul(q.beta, ldg_fr(q.S2 + j)))),
                         fp_add(cg, fp_mul(q.beta, ldg_fr(q.S3 + j)))),
@@ -301,7 +329,7 @@ __global__ void __launch_bounds__(128) k_quotient(QuotientArgs q, Fr* T) {
   Fr perm = fp_mul(q.alpha, fp_sub(p1, p2));
   Fr l0 = fp_mul(q.alpha2, fp_mul(fp_sub(z, q.one), ldg_fr(q.L0 + j)));
   Fr num = fp_add(fp_add(gate, perm), l0);
-  T[j] = fp_mul(num, q.zh_inv[j & 3]);
+  T[j] = fp_mul(num, q.zh_inv[(j * q.world + q.rank) & 3]);
 }
 
 // number of non-zero entries among v[0..n)
@@ -346,9 +374,10 @@ __global__ void k_l0_num(const Fr* X, uint64_t n4, Fr n_mont, Fr one, Fr* den) {
   if (j < n4) den[j] = fp_mul(n_mont, fp_sub(ldg_fr(X + j), one));
 }
 struct Four { Fr v[4]; };
-__global__ void k_scale_by4(Fr* v, uint64_t n4, Four m) {
+// v[j] *= m[(global coset index of j) mod 4], global index = world * j + rank
+__global__ void k_scale_by4(Fr* v, uint64_t n4, Four m, uint32_t world, uint32_t rank) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n4) v[j] = fp_mul(v[j], m.v[j & 3]);
+  if (j < n4) v[j] = fp_mul(v[j], m.v[(j * world + rank) & 3]);
 }
 __global__ void k_negate(Fr* v, uint64_t n) {
   uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,8 +394,11 @@ static void upload_mont(Context* ctx, DevBuf& dst, const uint8_t* h, uint64_t n)
   fr_to_mont(ctx, dst.as<Fr>(), dst.as<Fr>(), n);
 }
 
-// h_pk: 8 vectors (QM QL QR QO QC S1 S2 S3), each n x 32 bytes canonical (compiler/program.py:10-30)
-Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk) {
+Comm* ctx_comm(Context* ctx);
+
+// h_pk: 8 vectors (QM QL QR QO QC S1 S2 S3), each n x 32 bytes canonical (compiler/program.py:10-30).
+// sharded: one proof across the ranks of the context's communicator (see Prover in prover.cuh).
+Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h_pk, bool sharded) {
   auto P = std::make_unique<Prover>();
   P->ctx = ctx;
   P->srs = srs;
@@ -375,22 +407,41 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
   P->n = n;
   PB_CHECK(log_n >= 1 && log_n <= 26, "group order must be 2^k, 1 <= k <= 26");
   PB_CHECK(n <= srs_size(srs), "Not enough powers in setup");
+  if (sharded) {
+    Comm* cm = ctx_comm(ctx);
+    P->world = comm_world(cm);
+    P->rank = comm_rank(cm);
+    P->log_world = comm_log_world(cm);
+    PB_CHECK(log_n > P->log_world, "sharded prover: fewer rows than ranks");
+  }
+  const uint32_t G = (uint32_t)P->world, R = (uint32_t)P->rank;
+  P->log_ext = log_n + 2 - P->log_world;
+  const uint64_t ne = P->n_ext = (uint64_t)1 << P->log_ext;
+  P->fold = ne < n ? (uint32_t)(n / ne) : 1;
+  P->zw_separate = (4 % G) != 0;
+  P->zw_shift = P->zw_separate ? 0 : 4 / G;
   cudaStream_t st = ctx->stream;
   P->g = fr_from_u64(5);
   P->g_inv = fp_inv(P->g);
   Fr one = Fr::one();
+  const Fr mu = fr_root_of_unity(log_n + 2);
+  const Fr shift = fp_mul(P->g, fp_pow_u64(mu, R));  // this rank's slice is shift * <mu^world>
   // tables
   P->roots.alloc(n * 32);
   launch_powers(ctx, P->roots.as<Fr>(), n, fr_root_of_unity(log_n), one);
   P->gpow.alloc(n * 32);
-  launch_powers(ctx, P->gpow.as<Fr>(), n, P->g, one);
+  launch_powers(ctx, P->gpow.as<Fr>(), n, shift, one);
+  if (P->zw_separate) {
+    P->gpow_w.alloc(n * 32);
+    launch_powers(ctx, P->gpow_w.as<Fr>(), n, fp_mul(shift, fr_root_of_unity(log_n)), one);
+  }
   P->ginv_pow.alloc(n4 * 32);
   launch_powers(ctx, P->ginv_pow.as<Fr>(), n4, P->g_inv, one);
-  P->xs.alloc(n4 * 32);
-  launch_powers(ctx, P->xs.as<Fr>(), n4, fr_root_of_unity(log_n + 2), P->g);
-  // Z_H on the coset takes 4 values: g^n * i^(j mod 4) - 1, i = mu^n
+  P->xs.alloc(ne * 32);
+  launch_powers(ctx, P->xs.as<Fr>(), ne, fp_pow_u64(mu, G), shift);
+  // Z_H on the coset takes 4 values: g^n * i^(j mod 4) - 1, i = mu^n, j the global coset index
   Fr gn = fp_pow_u64(P->g, n);
-  Fr i4 = fp_pow_u64(fr_root_of_unity(log_n + 2), n);
+  Fr i4 = fp_pow_u64(mu, n);
   Four zh;
   Fr cur = gn;
   for (int k = 0; k < 4; k++) {
@@ -399,13 +450,13 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
     cur = fp_mul(cur, i4);
   }
   // L0(x_j) = (x_j^n - 1) / (n (x_j - 1))
-  P->l0_ext.alloc(n4 * 32);
+  P->l0_ext.alloc(ne * 32);
   {
-    DevBuf den(n4 * 32);
-    k_l0_num<<<PB_GRID(n4, 256), 0, st>>>(P->xs.as<Fr>(), n4, fr_from_u64(n), one, den.as<Fr>());
-    uint64_t T = (n4 + PB_BATCH_CH - 1) / PB_BATCH_CH;
-    k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), P->l0_ext.as<Fr>(), n4, T);
-    k_scale_by4<<<PB_GRID(n4, 256), 0, st>>>(P->l0_ext.as<Fr>(), n4, zh);
+    DevBuf den(ne * 32);
+    k_l0_num<<<PB_GRID(ne, 256), 0, st>>>(P->xs.as<Fr>(), ne, fr_from_u64(n), one, den.as<Fr>());
+    uint64_t T = (ne + PB_BATCH_CH - 1) / PB_BATCH_CH;
+    k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), P->l0_ext.as<Fr>(), ne, T);
+    k_scale_by4<<<PB_GRID(ne, 256), 0, st>>>(P->l0_ext.as<Fr>(), ne, zh, G, R);
     ctx->launches += 3;
     PB_CUDA(cudaStreamSynchronize(st));
   }
@@ -413,13 +464,19 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
     upload_mont(ctx, P->sel_lag[k], h_pk[k], n);
     P->sel_coeff[k].alloc(n * 32);
     ntt_run(ctx, P->sel_lag[k].as<Fr>(), P->sel_coeff[k].as<Fr>(), log_n, true, n, nullptr, nullptr);
-    P->sel_ext[k].alloc(n4 * 32);
-    ntt_run(ctx, P->sel_coeff[k].as<Fr>(), P->sel_ext[k].as<Fr>(), log_n + 2, false, n, P->gpow.as<Fr>(), nullptr);
+    P->sel_ext[k].alloc(ne * 32);
+    coset_extend(P.get(), st, nullptr, P->sel_coeff[k].as<Fr>(), P->sel_ext[k].as<Fr>(), P->gpow.as<Fr>());
   }
   for (int k = 0; k < 4; k++) P->lag[k].alloc(n * 32);
-  for (int k = 0; k < 5; k++) { P->coeff[k].alloc(n * 32); P->ext[k].alloc(n4 * 32); }
+  for (int k = 0; k < 5; k++) { P->coeff[k].alloc(n * 32); P->ext[k].alloc(ne * 32); }
+  if (P->zw_separate) P->ext[5].alloc(ne * 32);
   P->pi_lag.alloc(n * 32);
-  P->tq.alloc(n4 * 32);
+  if (P->world > 1) {
+    P->tq.alloc(3 * n * 32);
+    P->tq_loc.alloc(ne * 32);
+  } else {
+    P->tq.alloc(n4 * 32);
+  }
   for (int k = 0; k < 5; k++) P->tmp[k].alloc(n * 32);
   P->flags.alloc(64);
   if (const char* e = getenv("PB200_OVERLAP")) P->overlap = atoi(e) != 0;
@@ -429,13 +486,6 @@ Prover* prover_create(Context* ctx, Srs* srs, int log_n, const uint8_t* const* h
 }
 
 void prover_destroy(Prover* p) { delete p; }
-
-void prover_set_shard(Prover* P, uint64_t first, uint64_t count, bool enable) {
-  PB_CHECK(!enable || first + count <= P->n, "shard exceeds the group order");
-  P->sharded = enable;
-  P->shard_first = first;
-  P->shard_count = count;
-}
 
 static uint32_t read_flag(Prover* P, int idx) {
   uint32_t v;
@@ -483,23 +533,23 @@ static void store_canonical(uint8_t* dst, const Fr& mont) {
 // cached per prover: basis_i[j] = L_i(x_j) on the fixed coset for the first `count` rows
 static void ensure_pi_basis(Prover* P, int count) {
   Context* ctx = P->ctx;
-  const uint64_t n = P->n, n4 = 4 * n;
+  const uint64_t n = P->n, ne = P->n_ext;
   cudaStream_t st = ctx->stream;
   if ((int)P->pi_basis.size() >= count) return;
   Fr w = fr_root_of_unity(P->log_n);
   Fr gn = fp_pow_u64(P->g, n), i4 = fp_pow_u64(fr_root_of_unity(P->log_n + 2), n), one = Fr::one();
-  DevBuf den(n4 * 32);
+  DevBuf den(ne * 32);
   for (int i = (int)P->pi_basis.size(); i < count; i++) {
     Fr wi = fp_pow_u64(w, (uint64_t)i);
     Four zh;  // w^i (x_j^n - 1): four values
     Fr cur = gn;
     for (int k = 0; k < 4; k++) { zh.v[k] = fp_mul(wi, fp_sub(cur, one)); cur = fp_mul(cur, i4); }
-    P->pi_basis.emplace_back(n4 * 32);
+    P->pi_basis.emplace_back(ne * 32);
     Fr* out = P->pi_basis.back().as<Fr>();
-    k_lagrange_den<<<PB_GRID(n4, 256), 0, st>>>(P->xs.as<Fr>(), n4, wi, fr_from_u64(n), den.as<Fr>());
-    uint64_t T = (n4 + PB_BATCH_CH - 1) / PB_BATCH_CH;
-    k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), out, n4, T);
-    k_scale_by4<<<PB_GRID(n4, 256), 0, st>>>(out, n4, zh);
+    k_lagrange_den<<<PB_GRID(ne, 256), 0, st>>>(P->xs.as<Fr>(), ne, wi, fr_from_u64(n), den.as<Fr>());
+    uint64_t T = (ne + PB_BATCH_CH - 1) / PB_BATCH_CH;
+    k_batch_div<<<PB_GRID(T, 128), 0, st>>>(nullptr, den.as<Fr>(), out, ne, T);
+    k_scale_by4<<<PB_GRID(ne, 256), 0, st>>>(out, ne, zh, (uint32_t)P->world, (uint32_t)P->rank);
     ctx->launches += 3;
   }
   PB_CUDA(cudaStreamSynchronize(st));
@@ -512,6 +562,12 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
   const uint64_t n = P->n;
   cudaStream_t st = ctx->stream;
   PB_CHECK(n_public <= n, "more public inputs than rows");
+  if (ctx->aux_stream) {
+    // a previous proof that failed a check may have left coset extensions running on the side stream: everything
+    // this proof writes is ordered after them
+    PB_CUDA(cudaEventRecord(ctx->aux_ev[2], ctx->aux_stream));
+    PB_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[2], 0));
+  }
   const uint8_t* src[3] = {hA, hB, hC};
   if (wires_on_device) {
     for (int k = 0; k < 3; k++) fr_to_mont(ctx, reinterpret_cast<const Fr*>(src[k]), P->lag[k].as<Fr>(), n);
@@ -531,9 +587,11 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     for (int k = 0; k < 3; k++) {
       PB_CUDA(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
       fr_to_mont(ctx, P->lag[k].as<Fr>(), P->lag[k].as<Fr>(), n);
-      ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+      if (P->world == 1) ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
     }
   }
+  const Fr* abc_lag[3] = {P->lag[0].as<Fr>(), P->lag[1].as<Fr>(), P->lag[2].as<Fr>()};
+  Fr* abc_coeff[3] = {P->coeff[0].as<Fr>(), P->coeff[1].as<Fr>(), P->coeff[2].as<Fr>()};
   // PI: Lagrange values -public_i (prover.py:57-62)
   PB_CUDA(cudaMemsetAsync(P->pi_lag.p, 0, n * 32, st));
   if (n_public) {
@@ -548,9 +606,7 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
                                           P->sel_lag[Prover::QM].as<Fr>(), P->sel_lag[Prover::QO].as<Fr>(),
                                           P->sel_lag[Prover::QC].as<Fr>(), P->pi_lag.as<Fr>(), n, P->flags.as<uint32_t>());
   ctx->launches++;
-  if (wires_on_device)
-    for (int k = 0; k < 3; k++)
-      ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  if (wires_on_device || P->world > 1) interpolate(P, abc_lag, abc_coeff, 3);
   // public inputs: few of them -> PI is a short combination of cached Lagrange-basis vectors (no transforms);
   // otherwise fall back to interpolating PI like any other column
   P->n_public = n_public;
@@ -564,7 +620,9 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
       P->pub_neg[i] = fp_neg(fp_to_mont(v));
     }
   } else {
-    ntt_run(ctx, P->pi_lag.as<Fr>(), P->coeff[4].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+    const Fr* pl = P->pi_lag.as<Fr>();
+    Fr* pc = P->coeff[4].as<Fr>();
+    interpolate(P, &pl, &pc, 1);
   }
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
   if (P->overlap) launch_coset_ext_async(P, 0, 3, 0);
@@ -597,7 +655,11 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c) {
   ctx->launches += 5;
   Fr total;
   PB_CUDA(cudaMemcpyAsync(&total, tiles + n_tiles, 32, cudaMemcpyDeviceToHost, st));
-  ntt_run(ctx, P->lag[3].as<Fr>(), P->coeff[3].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
+  {
+    const Fr* zl = P->lag[3].as<Fr>();
+    Fr* zc = P->coeff[3].as<Fr>();
+    interpolate(P, &zl, &zc, 1);
+  }
   PB_CUDA(cudaStreamSynchronize(st));
   PB_CHECK(total == Fr::one(), "AssertionError: permutation grand product does not close, Z_n != 1 (prover.py:132)");
   if (P->overlap) launch_coset_ext_async(P, 3, 1, 1);
@@ -607,7 +669,7 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c) {
 // ---- round 3 (prover.py:154-226) -------------------------------------------------------------------------
 void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
   Context* ctx = P->ctx;
-  const uint64_t n = P->n, n4 = 4 * n;
+  const uint64_t n = P->n, n4 = 4 * n, ne = P->n_ext;
   cudaStream_t st = ctx->stream;
   P->alpha = fp_to_mont(alpha_c);
   P->fft_cofactor = fp_to_mont(cofactor_c);
@@ -615,12 +677,19 @@ void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
     PB_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[0], 0));
     PB_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));
   }
-  for (int k = (P->overlap ? 4 : 0); k < (P->pi_sparse ? 4 : 5); k++)
-    ntt_run(ctx, P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->log_n + 2, false, n, P->gpow.as<Fr>(), nullptr);
+  for (int k = (P->overlap ? 4 : 0); k < (P->pi_sparse ? 4 : 5); k++) {
+    coset_extend(P, st, nullptr, P->coeff[k].as<Fr>(), P->ext[k].as<Fr>(), P->gpow.as<Fr>());
+    if (k == 3 && P->zw_separate)
+      coset_extend(P, st, nullptr, P->coeff[3].as<Fr>(), P->ext[5].as<Fr>(), P->gpow_w.as<Fr>());
+  }
   QuotientArgs q;
   q.pi_cnt = P->pi_sparse ? (int)P->n_public : 0;
   for (int i = 0; i < q.pi_cnt; i++) { q.pi_basis[i] = P->pi_basis[i].as<Fr>(); q.pi_coef[i] = P->pub_neg[i]; }
   q.A = P->ext[0].as<Fr>(); q.B = P->ext[1].as<Fr>(); q.C = P->ext[2].as<Fr>(); q.Z = P->ext[3].as<Fr>();
+  q.Zw = P->zw_separate ? P->ext[5].as<Fr>() : P->ext[3].as<Fr>();
+  q.zw_shift = P->zw_shift;
+  q.world = (uint32_t)P->world;
+  q.rank = (uint32_t)P->rank;
   q.PI = P->pi_sparse ? nullptr : P->ext[4].as<Fr>();
   q.QM = P->sel_ext[Prover::QM].as<Fr>(); q.QL = P->sel_ext[Prover::QL].as<Fr>(); q.QR = P->sel_ext[Prover::QR].as<Fr>();
   q.QO = P->sel_ext[Prover::QO].as<Fr>(); q.QC = P->sel_ext[Prover::QC].as<Fr>();
@@ -628,14 +697,24 @@ void prover_round3(Prover* P, const Fr& alpha_c, const Fr& cofactor_c) {
   q.L0 = P->l0_ext.as<Fr>(); q.X = P->xs.as<Fr>();
   for (int k = 0; k < 4; k++) q.zh_inv[k] = P->zh_inv[k];
   q.alpha = P->alpha; q.alpha2 = fp_sqr(P->alpha); q.beta = P->beta; q.gamma = P->gamma; q.one = Fr::one();
-  q.n4 = n4;
-  k_quotient<<<PB_GRID(n4, 128), 0, st>>>(q, P->tq.as<Fr>());
+  q.n4 = ne;
+  Fr* t_evals = P->world > 1 ? P->tq_loc.as<Fr>() : P->tq.as<Fr>();
+  k_quotient<<<PB_GRID(ne, 128), 0, st>>>(q, t_evals);
   ctx->launches++;
-  // back to coefficients: ifft(4n) then * g^-i (poly.py:169-177 with the fixed coset)
-  ntt_run(ctx, P->tq.as<Fr>(), P->tq.as<Fr>(), P->log_n + 2, true, n4, nullptr, P->ginv_pow.as<Fr>());
   PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
-  k_count_nonzero<<<PB_GRID(n, 256), 0, st>>>(P->tq.as<Fr>() + 3 * n, n, P->flags.as<uint32_t>());
-  ctx->launches++;
+  if (P->world > 1) {
+    // slab-sharded inverse over the 4n coset: the local inverse transform of the slice, ONE allgather, then the
+    // join multiplies g^-i in and keeps the 3n coefficients (the top n must vanish: prover.py:205-208)
+    const Fr* te = t_evals;
+    ntt_shard_local(ctx, &te, 1, P->log_n + 2, true, 1, 0);
+    ntt_shard_combine(ctx, ctx->gather.as<Fr>(), ne, P->tq.as<Fr>(), P->log_n + 2, true, 3 * n,
+                      P->ginv_pow.as<Fr>(), P->flags.as<uint32_t>());
+  } else {
+    // back to coefficients: ifft(4n) then * g^-i (poly.py:169-177 with the fixed coset)
+    ntt_run(ctx, P->tq.as<Fr>(), P->tq.as<Fr>(), P->log_n + 2, true, n4, nullptr, P->ginv_pow.as<Fr>());
+    k_count_nonzero<<<PB_GRID(n, 256), 0, st>>>(P->tq.as<Fr>() + 3 * n, n, P->flags.as<uint32_t>());
+    ctx->launches++;
+  }
   PB_CHECK(read_flag(P, 0) == 0, "AssertionError: quotient has degree >= 3n (prover.py:205-208)");
   const Fr* t123[3] = {P->tq.as<Fr>(), P->tq.as<Fr>() + n, P->tq.as<Fr>() + 2 * n};
   P->commit_batch(t123, 3, n, P->proof.pts[4]);

@@ -2,42 +2,60 @@
 
 Two modes:
 
-* replicas (bench.py's default at N > 1): proofs are independent units, every rank owns an SRS replica and
+* replicas (bench.py's headline at N > 1): proofs are independent units, every rank owns an SRS replica and
   proves its own instances -- no data-path collective.
 
-* one proof across the GPUs of a box -- the MSM join of north_star: every commitment
-  ``sum_i c_i [tau^i]G`` (setup.py:66-72) is sharded by **point range**; rank g computes the partial sum over
-  powers [g*n/G, (g+1)*n/G) on its GPU, the 128-byte XYZZ partials are exchanged with ONE allgather per round
-  (NCCL over NVLink on GPUs; gloo in the CPU tests), and every rank adds the G partials and converts to affine
-  (NCCL has no elliptic-curve reduction, so the "reduce" is allgather + local add).  All ranks therefore see
-  the same commitments, feed the same transcript and stay in lock step.  The transforms and element-wise
-  kernels are replicated on every rank in this mode (slab-sharded NTT is not implemented yet)."""
+* ONE proof across the GPUs of a box (north_star: "shard MSM ... and NTT by coefficient-slab ... with a single NCCL
+  allgather at the join"): every rank holds the witness, the circuit and an SRS replica and runs the same
+  ``Prover.prove``; inside the library (csrc/prover.cu, world > 1)
+    - rank r owns every G-th point of the 4n coset, so the coset extensions, the cached selector extensions and the
+      quotient are local and divide by G;
+    - Lagrange -> coefficient transforms are slab-sharded: local n/G-point transforms, ONE allgather, a G-point DFT
+      per element at the join (csrc/ntt_shard.cuh);
+    - every commitment splits its 2^(c-1) buckets over the ranks (accumulation AND reduction divide by G), with ONE
+      allgather of 256 bytes per rank at the join (csrc/msm.cu).
+  The collectives are issued by the library itself on its CUDA stream through its own NCCL communicator
+  (csrc/comm.cu); ``torch.distributed`` only carries the 128-byte rendezvous id (``init_comm``).  All ranks see the
+  same commitments, feed the same transcript and return the same 768 bytes."""
 from __future__ import annotations
 
 import ctypes
 from typing import Optional
 
-import numpy as np
-
 from . import _lib
-from .prover import Prover, _pts
+from .prover import Prover
 
 
 def shard_range(n: int, rank: int, world: int):
-    """Contiguous point range [first, first+count) of rank `rank` out of `world` (the first n % world ranks
-    get one extra point)."""
+    """Contiguous range [first, first+count) of rank `rank` out of `world` (the first n % world ranks get one
+    extra item): the point-range cut of pb200_srs_commit_partial."""
     base, extra = divmod(n, world)
     first = rank * base + min(rank, extra)
     return first, base + (1 if rank < extra else 0)
 
 
+def bucket_range(n_buckets: int, rank: int, world: int):
+    """Bucket magnitudes [lo, hi) of rank `rank`: the even split the library uses for sharded commitments."""
+    per = n_buckets // world
+    return rank * per, (rank + 1) * per
+
+
 def combine_partials(parts: bytes, count: int):
-    """Sum `count` XYZZ partial sums (128 bytes each, as produced by pb200_prover_read_partials) into one
-    affine point; returns (x||y little-endian bytes, is_identity).  Host arithmetic inside the library."""
+    """Sum `count` XYZZ partial sums (128 bytes each, as produced by pb200_srs_commit_partial) into one affine
+    point; returns (x||y little-endian bytes, is_identity).  Host arithmetic inside the library."""
     out = ctypes.create_string_buffer(64)
     ident = ctypes.c_int(0)
     _lib.check(_lib.lib().pb200_g1_combine_partials_host(parts, count, out, ctypes.byref(ident)))
     return out.raw, bool(ident.value)
+
+
+def join_bucket_shards(sr: bytes, world: int, sets: int, nloc: int):
+    """Host half of the sharded commitment's join: `sr` = [world][sets] (S, R) pairs of 2 x 128 bytes; returns a list
+    of (x||y bytes, is_identity) per set."""
+    out = ctypes.create_string_buffer(64 * sets)
+    ident = (ctypes.c_int * sets)()
+    _lib.check(_lib.lib().pb200_g1_join_bucket_shards_host(sr, world, sets, nloc, out, ident))
+    return [(out.raw[64 * k:64 * k + 64], bool(ident[k])) for k in range(sets)]
 
 
 def allgather_bytes(local: bytes, group=None, device=None) -> list:
@@ -54,103 +72,88 @@ def allgather_bytes(local: bytes, group=None, device=None) -> list:
     return [o.cpu().numpy().tobytes() for o in outs]
 
 
-class ShardedProver(Prover):
-    """``Prover`` whose commitments are point-sharded across the ranks of a process group."""
-
-    @classmethod
-    def from_arrays(cls, setup, group_order, pk_arrays, group=None):
-        self = super().from_arrays(setup, group_order, pk_arrays)
-        self._init_shard(group)
-        return self
-
-    def __init__(self, setup, program, group=None):
-        super().__init__(setup, program)
-        self._init_shard(group)
-
-    def _init_shard(self, group):
-        import torch
-        import torch.distributed as dist
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-        first, count = shard_range(self.group_order, self.rank, self.world)
-        _lib.check(_lib.lib().pb200_prover_set_shard(self._h, first, count, 1))
-        self._device = torch.device("cuda", self.ctx.device)
-
-    def _commitments(self, first_slot: int, count: int, raw: bytes):
-        buf = ctypes.create_string_buffer(128 * count)
-        _lib.check(_lib.lib().pb200_prover_read_partials(self._h, first_slot, count, buf))
-        gathered = allgather_bytes(buf.raw, self.group, self._device)  # the one collective of this round
-        xy = b""
-        for k in range(count):
-            parts = b"".join(g[128 * k:128 * (k + 1)] for g in gathered)
-            pt, ident = combine_partials(parts, self.world)
-            if ident:
-                raise _lib.PlonkB200Error("commitment is the point at infinity (unsupported by the reference transcript)")
-            xy += pt
-        _lib.check(_lib.lib().pb200_prover_set_points(self._h, first_slot, count, xy))
-        return _pts(xy, count)
-
-    def prove_arrays(self, A, B, C, public) -> bytes:
-        """Round-by-round (the commitments need the collective between rounds); returns the 768-byte proof."""
-        from .curve import Scalar
-        from .prover import _as_le_rows
-        from .transcript import Transcript
-        n = self.group_order
-        a, b, c = (_as_le_rows(v, n) for v in (A, B, C))
-        pub = _as_le_rows(public, len(public)) if len(public) else np.zeros((0, 32), dtype=np.uint8)
-        vp = ctypes.c_void_p
-        L = _lib.lib()
-        tr = Transcript(b"plonk")
-        out = ctypes.create_string_buffer(192)
-        _lib.check(L.pb200_prover_round1(self._h, a.ctypes.data_as(vp), b.ctypes.data_as(vp), c.ctypes.data_as(vp),
-                                         pub.ctypes.data_as(vp), pub.shape[0], out))
-        from .transcript import Message1, Message2, Message3, Message5
-        self.beta, self.gamma = tr.round_1(Message1(*self._commitments(0, 3, out.raw)))
-        msg2 = self.round_2()
-        self.alpha, self.fft_cofactor = tr.round_2(msg2)
-        msg3 = self.round_3()
-        self.zeta = tr.round_3(msg3)
-        msg4 = self.round_4()
-        self.v = tr.round_4(msg4)
-        self.round_5()
-        proof = ctypes.create_string_buffer(768)
-        _lib.check(L.pb200_prover_serialize(self._h, proof))
-        return proof.raw
+def broadcast_bytes(payload: Optional[bytes], size: int, src: int = 0, group=None, device=None) -> bytes:
+    """Rank `src` sends `payload` (`size` bytes) to every rank of the group (NCCL when `device` is given, else gloo)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(size, dtype=torch.uint8)
+    if dist.get_rank(group) == src:
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return t.cpu().numpy().tobytes()
 
 
-# ------------------------------------------------------------------------------------------------
-# slab-sharded NTT (north_star: "NTT by coefficient-slab across the GPUs with a single allgather at the join")
-# ------------------------------------------------------------------------------------------------
-def slab_ntt_plan(log_n: int, world: int):
-    """N = 2^log_n over `world` = 2^log_g ranks -> (log_m, log_g): rank h owns the decimated input x[h::world]
-    and produces the contiguous output slab [h*M, (h+1)*M), M = N / world."""
-    log_g = world.bit_length() - 1
-    assert world == 1 << log_g and 1 <= log_g <= 3 and log_n > log_g, "slab NTT: 2, 4 or 8 ranks"
-    return log_n - log_g, log_g
-
-
-def slab_ntt(x_full, log_n: int, inverse: bool = False, group=None, ctx: Optional[_lib.Context] = None):
-    """Distributed NTT of the length-2^log_n vector `x_full` (a CUDA uint8/int32 tensor of N*32 bytes holding
-    canonical or Montgomery Fr elements, present on every rank; only the rank's decimated part is read).
-    Returns this rank's contiguous output slab as a CUDA tensor [M, 32] uint8.  One NCCL allgather."""
+def init_comm(ctx: Optional[_lib.Context] = None, group=None) -> _lib.Context:
+    """Give the library context its own NCCL communicator over the ranks of `group` (default: the world group):
+    rank 0 draws the id, torch.distributed carries it, every rank joins.  Idempotent per context."""
     import torch
     import torch.distributed as dist
     ctx = ctx or _lib.default_context()
+    if getattr(ctx, "comm_world", 1) > 1:
+        return ctx
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    log_m, log_g = slab_ntt_plan(log_n, world)
-    M = 1 << log_m
     L = _lib.lib()
+    uid = ctypes.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(L.pb200_comm_unique_id(uid))
+    device = torch.device("cuda", ctx.device) if dist.get_backend(group) == "nccl" else None
+    raw = broadcast_bytes(uid.raw if rank == 0 else None, 128, 0, group, device)
+    _lib.check(L.pb200_comm_init(ctx.handle, raw, rank, world))
+    ctx.comm_rank, ctx.comm_world = rank, world
+    return ctx
+
+
+def comm_info(ctx: _lib.Context):
+    """(rank, world, collectives issued, bytes received) of the context's communicator"""
+    r, w = ctypes.c_int(), ctypes.c_int()
+    c, b = ctypes.c_uint64(), ctypes.c_uint64()
+    _lib.check(_lib.lib().pb200_comm_info(ctx.handle, ctypes.byref(r), ctypes.byref(w), ctypes.byref(c), ctypes.byref(b)))
+    return r.value, w.value, c.value, b.value
+
+
+class ShardedProver(Prover):
+    """``Prover`` for one proof across the ranks of a process group: same constructor arguments, same methods,
+    same bytes.  Every rank must make the same calls with the same inputs (the collectives inside are matched
+    pairwise); the context needs a communicator (``init_comm``)."""
+    _CREATE = "pb200_prover_create_sharded"
+
+    @classmethod
+    def from_arrays(cls, setup, group_order, pk_arrays, group=None, ctx=None):
+        init_comm(ctx or setup.ctx, group)
+        return super().from_arrays(setup, group_order, pk_arrays, ctx=ctx)
+
+    def __init__(self, setup, program, group=None):
+        init_comm(setup.ctx, group)
+        super().__init__(setup, program)
+
+
+# ------------------------------------------------------------------------------------------------
+# operators (BASELINE.json metric: Fr-NTT elems/s and G1-MSM pts/s at 1/2/4/8 GPUs)
+# ------------------------------------------------------------------------------------------------
+def sharded_ntt(x_full, log_n: int, inverse: bool = False, ctx: Optional[_lib.Context] = None, out=None):
+    """Distributed NTT of the length-2^log_n vector `x_full` (a CUDA tensor of N*32 bytes, present on every rank;
+    only the rank's decimated part x[rank::world] is read).  Returns the FULL transform on every rank (a CUDA tensor
+    [N, 32] uint8).  One NCCL allgather, issued by the library.  The context must carry a communicator."""
+    import torch
+    ctx = ctx or _lib.default_context()
+    n = 1 << log_n
+    if out is None:
+        out = torch.empty((n, 32), dtype=torch.uint8, device=x_full.device)
     vp = ctypes.c_void_p
-    local = torch.empty((M, 32), dtype=torch.uint8, device=x_full.device)
-    _lib.check(L.pb200_fr_ntt_decimated(ctx.handle, vp(x_full.data_ptr()), vp(local.data_ptr()), log_m,
-                                        1 if inverse else 0, world, rank))
-    ctx.sync()  # the library stream is not torch's: make the sub-spectrum visible to the collective
-    sub = torch.empty((world, M, 32), dtype=torch.uint8, device=x_full.device)
-    dist.all_gather_into_tensor(sub, local, group=group)  # the one exchange step
-    torch.cuda.current_stream().synchronize()
-    out = torch.empty((M, 32), dtype=torch.uint8, device=x_full.device)
-    _lib.check(L.pb200_fr_ntt_slab_combine(ctx.handle, vp(sub.data_ptr()), vp(out.data_ptr()), log_m, log_g, rank,
-                                           1 if inverse else 0))
-    ctx.sync()
+    _lib.check(_lib.lib().pb200_fr_ntt_sharded(ctx.handle, vp(x_full.data_ptr()), vp(out.data_ptr()), log_n,
+                                               1 if inverse else 0))
     return out
+
+
+def sharded_commit(setup, coeffs, m: int, montgomery: bool = False):
+    """setup.py:66-72's MSM over device-resident coefficients `coeffs` (CUDA tensor, m*32 bytes, on every rank) with
+    the buckets split over the ranks; returns ((x, y) ints or None).  One NCCL allgather of 256 bytes per rank."""
+    out = ctypes.create_string_buffer(64)
+    ident = ctypes.c_int()
+    _lib.check(_lib.lib().pb200_srs_commit_coeffs_sharded(setup.ctx.handle, setup._srs, ctypes.c_void_p(coeffs.data_ptr()),
+                                                          m, 1 if montgomery else 0, out, ctypes.byref(ident)))
+    if ident.value:
+        return None
+    return int.from_bytes(out.raw[:32], "little"), int.from_bytes(out.raw[32:], "little")

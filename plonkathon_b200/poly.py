@@ -1,7 +1,9 @@
 """Drop-in for the reference's ``poly.py``: ``Basis`` and ``Polynomial`` with the same methods,
 assertions and list-of-Scalar ``.values`` (poly.py:10-195).  The transforms run on the GPU
-(csrc/ntt.cu) through the host-buffer C ABI; element-wise ring ops stay list-based like the
-reference (they are not on the accelerated path -- the prover uses device-resident vectors)."""
+(csrc/ntt.cu); the element-wise ring operations run on the GPU too (csrc/poly_ops.cu, pb200_fr_vec_op) whenever an
+operand is device-resident -- the result of a transform, a round's state read off the prover -- so a
+reference-style round written with Polynomial arithmetic (prover.py:188-202) never materialises 2^k Scalars; plain
+list operands keep the reference's list arithmetic."""
 from __future__ import annotations
 
 import ctypes
@@ -53,8 +55,11 @@ class Polynomial:
 
     @property
     def values(self):
+        """The reference's list[Scalar].  Reading it makes the list the source of truth, as in the reference: the HBM
+        copy is dropped, so in-place edits of the list are seen by every later transform / commitment."""
         if self._values is None:
             self._values = bytes_to_scalars(self._dev.cpu().numpy().tobytes())
+        self._dev = None
         return self._values
 
     @values.setter
@@ -65,58 +70,105 @@ class Polynomial:
     def __len__(self):
         return len(self._values) if self._values is not None else int(self._dev.shape[0])
 
+    @property
+    def on_device(self) -> bool:
+        return self._dev is not None
+
     def _device(self, ctx):
-        """canonical [n, 32] uint8 CUDA tensor holding the values (uploaded once)"""
+        """canonical [n, 32] uint8 CUDA tensor holding the values, on the context's device (uploaded once)"""
         import torch
+        dev = torch.device("cuda", ctx.device)
+        if self._dev is not None and self._dev.device != dev:
+            self._dev = self._dev.to(dev)
         if self._dev is None:
             raw = bytearray(scalars_to_bytes(self._values))
             t = torch.frombuffer(raw, dtype=torch.uint8).reshape(-1, 32) if raw else torch.empty((0, 32), dtype=torch.uint8)
-            self._dev = t.to(torch.device("cuda", ctx.device))
-            torch.cuda.current_stream(self._dev.device).synchronize()  # the library runs on its own stream
+            self._dev = t.to(dev)
+            torch.cuda.current_stream(dev).synchronize()  # the library runs on its own stream
         return self._dev
 
     def __eq__(self, other):
-        return (self.basis == other.basis) and (self.values == other.values)
+        if self.basis != other.basis:
+            return False
+        if self.on_device and other.on_device and self._dev.device == other._dev.device:
+            import torch
+            return self._dev.shape == other._dev.shape and bool(torch.equal(self._dev, other._dev))
+        if self.on_device or other.on_device:  # compare bytes without building 2^k Scalars on the resident side
+            if len(self) != len(other):
+                return False
+            raw = lambda p: p._dev.cpu().numpy().tobytes() if p.on_device else scalars_to_bytes(p._values)  # noqa: E731
+            return raw(self) == raw(other)
+        return self.values == other.values
 
-    # ---- ring operations (poly.py:23-100)
-    def _zip(self, other, op, lagrange_only=False):
-        assert len(self.values) == len(other.values)
+    # ---- ring operations (poly.py:23-109)
+    # op codes of pb200_fr_vec_op
+    _ADD, _SUB, _MUL, _DIV, _ADD_S, _SUB_S, _MUL_S, _ADD_S0, _SUB_S0, _SHIFT = range(10)
+
+    def _vec(self, op, other=None, scalar=None, shift=0, ctx=None):
+        """one element-wise kernel over device-resident canonical vectors; the result stays in HBM"""
+        import torch
+        ctx = self._ctx(ctx)
+        a = self._device(ctx)
+        b = other._device(ctx) if other is not None else None
+        out = torch.empty_like(a)
+        torch.cuda.current_stream(a.device).synchronize()
+        sb = (int(scalar) % CURVE_ORDER).to_bytes(32, "little") if scalar is not None else None
+        _lib.check(_lib.lib().pb200_fr_vec_op(ctx.handle, op, ctypes.c_void_p(a.data_ptr()),
+                                              ctypes.c_void_p(b.data_ptr()) if b is not None else None, sb,
+                                              ctypes.c_void_p(out.data_ptr()), len(self), shift))
+        ctx.sync()
+        return Polynomial(None, self.basis, _dev=out)
+
+    def _zip(self, other, op, dev_op, lagrange_only=False):
+        assert len(self) == len(other)
         assert self.basis == other.basis
         if lagrange_only:
             assert self.basis == Basis.LAGRANGE
+        if self.on_device or other.on_device:
+            return self._vec(dev_op, other)
         return Polynomial([op(x, y) for x, y in zip(self.values, other.values)], self.basis)
 
     def __add__(self, other):
         if isinstance(other, Polynomial):
-            return self._zip(other, lambda x, y: x + y)
+            return self._zip(other, lambda x, y: x + y, self._ADD)
         assert isinstance(other, Scalar)
+        if self.on_device:
+            return self._vec(self._ADD_S if self.basis == Basis.LAGRANGE else self._ADD_S0, scalar=other.n)
         if self.basis == Basis.LAGRANGE:
             return Polynomial([x + other for x in self.values], self.basis)
         return Polynomial([self.values[0] + other] + self.values[1:], self.basis)
 
     def __sub__(self, other):
         if isinstance(other, Polynomial):
-            return self._zip(other, lambda x, y: x - y)
+            return self._zip(other, lambda x, y: x - y, self._SUB)
         assert isinstance(other, Scalar)
+        if self.on_device:
+            return self._vec(self._SUB_S if self.basis == Basis.LAGRANGE else self._SUB_S0, scalar=other.n)
         if self.basis == Basis.LAGRANGE:
             return Polynomial([x - other for x in self.values], self.basis)
         return Polynomial([self.values[0] - other] + self.values[1:], self.basis)
 
     def __mul__(self, other):
         if isinstance(other, Polynomial):
-            return self._zip(other, lambda x, y: x * y, lagrange_only=True)
+            return self._zip(other, lambda x, y: x * y, self._MUL, lagrange_only=True)
         assert isinstance(other, Scalar)
+        if self.on_device:
+            return self._vec(self._MUL_S, scalar=other.n)
         return Polynomial([x * other for x in self.values], self.basis)
 
     def __truediv__(self, other):
         if isinstance(other, Polynomial):
-            return self._zip(other, lambda x, y: x / y, lagrange_only=True)
+            return self._zip(other, lambda x, y: x / y, self._DIV, lagrange_only=True)
         assert isinstance(other, Scalar)
+        if self.on_device:
+            return self._vec(self._MUL_S, scalar=(Scalar(1) / other).n)  # py_ecc: x / 0 == 0
         return Polynomial([x / other for x in self.values], self.basis)
 
     def shift(self, shift: int):
         assert self.basis == Basis.LAGRANGE
-        assert shift < len(self.values)
+        assert shift < len(self)
+        if self.on_device:
+            return self._vec(self._SHIFT, shift=shift)
         return Polynomial(self.values[shift:] + self.values[:shift], self.basis)
 
     # ---- transforms (GPU)

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from .curve import Scalar
 from .field import CURVE_ORDER, FQ
-from .poly import _log2_exact, scalars_to_bytes
+from .poly import Basis, _log2_exact, scalars_to_bytes
 from .transcript import Message1, Message2, Message3, Message4, Message5, Transcript
 
 PK_ORDER = ("QM", "QL", "QR", "QO", "QC", "S1", "S2", "S3")  # compiler/program.py:10-30
@@ -84,6 +84,8 @@ def _raise(err: _lib.PlonkB200Error):
 
 
 class Prover:
+    _CREATE = "pb200_prover_create"
+
     def __init__(self, setup, program):
         """prover.py:45-49."""
         self.group_order = program.group_order
@@ -113,8 +115,8 @@ class Prover:
         keep = [c if isinstance(c, bytes) else c.tobytes() for c in (cols[k] for k in PK_ORDER)]
         arr = (ctypes.c_char_p * 8)(*keep)
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().pb200_prover_create(self.ctx.handle, setup._srs, self._log_n,
-                                                  ctypes.cast(arr, ctypes.c_void_p), ctypes.byref(h)))
+        create = getattr(_lib.lib(), self._CREATE)  # the multi-GPU prover creates its sharded counterpart
+        _lib.check(create(self.ctx.handle, setup._srs, self._log_n, ctypes.cast(arr, ctypes.c_void_p), ctypes.byref(h)))
         self._h = h
 
     def __del__(self):
@@ -165,6 +167,12 @@ class Prover:
         B = [int(witness[w.R]) % CURVE_ORDER for w in wires]
         C = [int(witness[w.O]) % CURVE_ORDER for w in wires]
         self._public = [int(witness[v]) % CURVE_ORDER for v in self.program.get_public_assignments()]
+        return self.round_1_arrays(A, B, C, self._public)
+
+    def round_1_arrays(self, A, B, C, public) -> Message1:
+        """round 1 from wire-value columns (lists of ints or (n,32) uint8 arrays) instead of a witness dict"""
+        n = self.group_order
+        self._public = [int(x) % CURVE_ORDER for x in public]
         a, b, c = (_as_le_rows(v, n) for v in (A, B, C))
         pub = _as_le_rows(self._public, len(self._public)) if self._public else np.zeros((0, 32), np.uint8)
         out = ctypes.create_string_buffer(192)
@@ -213,8 +221,29 @@ class Prover:
             _raise(e)
         return Message5(*self._commitments(7, 2, out.raw))
 
+    # ------------------------------------------------------------------ round state (prover.py: self.A .. self.T3)
+    def _state(self, which: int, basis):
+        """a vector of the device-resident round state as a lazily materialised Polynomial (stays in HBM)"""
+        import torch
+        from .poly import Polynomial
+        n = self.group_order
+        t = torch.empty((n, 32), dtype=torch.uint8, device=torch.device("cuda", self.ctx.device))
+        _lib.check(_lib.lib().pb200_prover_read_vector(self._h, which, ctypes.c_void_p(t.data_ptr())))
+        return Polynomial(None, basis, _dev=t)
+
+    A = property(lambda self: self._state(0, Basis.LAGRANGE), doc="prover.py:97-103 (after round_1)")
+    B = property(lambda self: self._state(1, Basis.LAGRANGE))
+    C = property(lambda self: self._state(2, Basis.LAGRANGE))
+    Z = property(lambda self: self._state(3, Basis.LAGRANGE), doc="prover.py:147 (after round_2)")
+    PI = property(lambda self: self._state(4, Basis.LAGRANGE), doc="prover.py:57-63 (after round_1)")
+    # T1, T2, T3 are Lagrange-basis Polynomials in the reference (prover.py:209-219): the forward transform of the
+    # three coefficient thirds the library keeps (after round_3)
+    T1 = property(lambda self: self._state(5, Basis.MONOMIAL).fft(ctx=self.ctx))
+    T2 = property(lambda self: self._state(6, Basis.MONOMIAL).fft(ctx=self.ctx))
+    T3 = property(lambda self: self._state(7, Basis.MONOMIAL).fft(ctx=self.ctx))
+
     def _commitments(self, first_slot: int, count: int, raw: bytes):
-        """commitments a round produced (overridden by the multi-GPU prover, which gathers partial sums)"""
+        """commitments a round produced"""
         return _pts(raw, count)
 
     def fft_expand(self, x):

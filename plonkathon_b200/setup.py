@@ -88,6 +88,13 @@ class Setup:
         return [(FQ(int.from_bytes(raw[64 * k:64 * k + 32], "little")),
                  FQ(int.from_bytes(raw[64 * k + 32:64 * k + 64], "little"))) for k in range(count)]
 
+    def export_points_array(self, first: int, count: int):
+        """the same points as a (count, 64) uint8 array (x || y little-endian), without building Python objects"""
+        import numpy as np
+        buf = np.empty((count, 64), dtype=np.uint8)
+        _lib.check(_lib.lib().pb200_srs_export(self.ctx.handle, self._srs, buf.ctypes.data_as(ctypes.c_void_p), first, count))
+        return buf
+
     @property
     def powers_of_x(self):
         if self._powers is None:

@@ -778,3 +778,100 @@ def test_prove_2p22_gates_against_golden(pb):
         assert raw.hex() == json.load(open(path))["proof_hex"]
     vk = setup.verification_key_arrays(n, pk)
     assert vk.verify_proof(n, pb.Proof.from_bytes(raw), [int(x) for x in public])
+
+
+# ------------------------------------------------------------------ ring operations and round state on the device
+def test_polynomial_ring_ops_on_device(pb):
+    """poly.py:23-109 on device-resident operands (pb200_fr_vec_op) against the reference's list arithmetic, which the
+    same class runs for plain-list operands: + - * / with a Polynomial or a Scalar, both bases, shift; a zero divisor
+    gives 0 (py_ecc's inv(0) == 0); mixed resident / list operands; in-place edits of .values are seen afterwards"""
+    rng = random.Random(21)
+    n = 1 << 10
+    va = [rng.randrange(R) for _ in range(n)]
+    vb = [rng.randrange(R) for _ in range(n)]
+    vb[3] = vb[700] = 0
+    s = pb.Scalar(rng.randrange(1, R))
+    L, M = pb.Basis.LAGRANGE, pb.Basis.MONOMIAL
+
+    def resident(v, basis):  # a Polynomial whose data lives in HBM only (the result of a transform)
+        p = pb.Polynomial(S(pb, v), L if basis == M else M)
+        q = p.ifft().fft() if basis == L else p.fft().ifft()  # round trip: same values, device-resident
+        assert q._values is None and q.on_device and q.basis == basis
+        return q
+
+    for basis in (L, M):
+        la, lb = pb.Polynomial(S(pb, va), basis), pb.Polynomial(S(pb, vb), basis)
+        ops = [lambda x, y: x + y, lambda x, y: x - y, lambda x, y: x + s, lambda x, y: x - s, lambda x, y: x * s,
+               lambda x, y: x / s, lambda x, y: x / pb.Scalar(0)]
+        if basis == L:
+            ops += [lambda x, y: x * y, lambda x, y: x / y, lambda x, y: x.shift(5), lambda x, y: x.shift(0),
+                    lambda x, y: (x * y + x * s - y) / (y + s)]
+        for k, op in enumerate(ops):
+            want = op(la, lb)
+            assert not want.on_device
+            for da, db in ((resident(va, basis), resident(vb, basis)), (resident(va, basis), lb), (la, resident(vb, basis))):
+                got = op(da, db)
+                if da.on_device:
+                    assert got.on_device and got._values is None, k
+                assert got.basis == basis and got == want and vals(got) == vals(want), (basis, k)
+    with pytest.raises(AssertionError):
+        resident(va, M) * resident(vb, M)  # element-wise product is a LAGRANGE-basis operation (poly.py:67)
+    # the list is the source of truth once it has been handed out
+    p = resident(va, L)
+    p.values[0] = pb.Scalar(123)
+    assert not p.on_device and vals(p.ifft().fft())[0] == 123
+
+
+def test_reference_style_round_3_through_the_facade(pb):
+    """prover.py:154-226 written the way the reference prescribes -- Polynomial arithmetic on the round state
+    self.A .. self.Z, fft_expand / expanded_evals_to_coeffs / rlc (prover.py:308-315) -- on 4n = 2^16 device-resident
+    values, against the library's own round 3: the same T1, T2, T3 (hence the same commitments), the degree check
+    of prover.py:205-208 and the T1/T2/T3 identity of prover.py:215-219."""
+    from plonkathon_b200 import synthetic as syn
+    from plonkathon_b200.transcript import Transcript
+    log_n = 14
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=5, n_public=3)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    prover = pb.Prover.from_arrays(setup, n, pk)
+    tr = Transcript(b"plonk")
+    prover.beta, prover.gamma = tr.round_1(prover.round_1_arrays(A, B, C, public))
+    prover.alpha, prover.fft_cofactor = tr.round_2(prover.round_2())
+    msg_3 = prover.round_3()
+    L = pb.Basis.LAGRANGE
+    one = pb.Scalar(1)
+    col = lambda k: pb.Polynomial([pb.Scalar(int.from_bytes(bytes(r), "little")) for r in pk[k]], L)  # noqa: E731
+    roots = [pb.Scalar(x) for x in O.roots_of_unity(n)]
+    # round state: device-resident Lagrange polynomials
+    sA, sB, sC, sZ, sPI = prover.A, prover.B, prover.C, prover.Z, prover.PI
+    assert all(p.on_device and p.basis == L and len(p) == n for p in (sA, sB, sC, sZ, sPI))
+    assert sA == pb.Polynomial([pb.Scalar(int.from_bytes(bytes(r), "little")) for r in A], L)
+    # the reference's round-1 sanity check (prover.py:108-116), on the device
+    zero = pb.Polynomial([pb.Scalar(0)] * n, L)
+    assert sA * col("QL") + sB * col("QR") + sA * sB * col("QM") + sC * col("QO") + sPI + col("QC") == zero
+    ex = prover.fft_expand
+    A_big, B_big, C_big, Z_big, PI_big = ex(sA), ex(sB), ex(sC), ex(sZ), ex(sPI)
+    ZW_big = Z_big.shift(4)
+    QL, QR, QM, QO, QC = (ex(col(k)) for k in ("QL", "QR", "QM", "QO", "QC"))
+    S1, S2, S3 = (ex(col(k)) for k in ("S1", "S2", "S3"))
+    cof = prover.fft_cofactor
+    mu = pb.Scalar(O.root_of_unity(4 * n))
+    quarter_roots = [cof * mu ** i for i in range(4 * n)]
+    X_big = pb.Polynomial(quarter_roots, L)
+    ZH_big = pb.Polynomial([x ** n - one for x in quarter_roots], L)
+    L0_big = ex(pb.Polynomial([one] + [pb.Scalar(0)] * (n - 1), L))
+    rlc, al = prover.rlc, prover.alpha
+    gate = A_big * QL + B_big * QR + A_big * B_big * QM + C_big * QO + PI_big + QC
+    perm = (rlc(A_big, X_big) * rlc(B_big, X_big * pb.Scalar(2)) * rlc(C_big, X_big * pb.Scalar(3))) * Z_big \
+        - (rlc(A_big, S1) * rlc(B_big, S2) * rlc(C_big, S3)) * ZW_big
+    QUOT_big = (gate + perm * al + (Z_big - one) * L0_big * (al * al)) / ZH_big
+    assert QUOT_big.on_device and len(QUOT_big) == 4 * n
+    coeffs = prover.expanded_evals_to_coeffs(QUOT_big)
+    cv = vals(coeffs)
+    assert cv[-n:] == [0] * n  # prover.py:205-208
+    T1, T2, T3 = prover.T1, prover.T2, prover.T3  # the library's round 3, as the reference's Lagrange polynomials
+    assert [vals(t.ifft()) for t in (T1, T2, T3)] == [cv[:n], cv[n:2 * n], cv[2 * n:3 * n]]
+    assert (T1.barycentric_eval(cof) + T2.barycentric_eval(cof) * cof ** n
+            + T3.barycentric_eval(cof) * cof ** (2 * n)) == QUOT_big.values[0]  # prover.py:215-219
+    assert (setup.commit(T1), setup.commit(T2), setup.commit(T3)) == (msg_3.t_lo_1, msg_3.t_mid_1, msg_3.t_hi_1)

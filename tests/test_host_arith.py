@@ -207,7 +207,7 @@ def test_msm_bucket_pipeline_on_host(lib):
     edge = [0, 1, 2, O.R_MOD - 1, O.R_MOD - 2, (1 << 253) + 5, 15, 16, 17, (1 << 128) - 1]
     rand = lambda: [rng.choice(edge) if rng.random() < 0.3 else rng.randrange(O.R_MOD) for _ in range(n)]
     # generic mode (one bucket set per window), several blockings
-    for c, B, g0 in ((4, 1, 2), (4, 5, 4), (5, 64, 16), (3, 2, 2)):
+    for c, B, g0 in ((4, 2, 2), (4, 5, 4), (5, 128, 16), (3, 3, 2)):
         sc = rand()
         got, _ = _msm_pipeline(lib, points, [sc], c, False, 0, 1 << 30, B, g0)
         assert got[0] == _oracle_msm(points, sc), (c, B, g0)
@@ -228,6 +228,10 @@ def test_msm_bucket_pipeline_on_host(lib):
             part, _ = _msm_pipeline(lib, points, vecs, 5, True, lo, hi, 4, 2)
             acc = [O.g1_add(a, p) for a, p in zip(acc, part)]
         assert acc == expect, cuts
+    # wide windows: 4096 buckets per window, two block-level chunks and a second block level in the reduction
+    sc = rand()
+    got, _ = _msm_pipeline(lib, points, [sc], 13, False, 0, 1 << 30, 16, 2)
+    assert got[0] == _oracle_msm(points, sc)
     # an empty result: all scalars zero
     got, _ = _msm_pipeline(lib, points, [[0] * n], 4, False, 0, 1 << 30, 4, 4)
     assert got == [None]
