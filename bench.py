@@ -546,7 +546,7 @@ def b200_arm(args):
     # dominant kernel group: the MSM bucket accumulation (rounds of batched affine additions: k_aff_round0 +
     # k_aff_round launches of one MSM call, bracketed by one event pair).  Algorithmic bytes: 96 B per point (64 B
     # affine point + 32 B scalar) x the points of the call.
-    xyzz = os.environ.get("PB200_MSM_ACC") == "xyzz"
+    xyzz = os.environ.get("PB200_MSM_ACC") != "affine"
     acc_avg_ms = acc_ms / max(1, acc_cnt)
     # 9 commitments x n points per proof go through the accumulation (4 batched MSM calls per proof)
     points_per_launch = 9.0 * n * args.steps / max(1, acc_cnt)

@@ -219,7 +219,7 @@ int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars,
   for (uint64_t t = 0; t < cur.size() + 3; t++) reduce_level0_thread(ra, t);
   uint32_t m = reduce_groups(ra.m, ra.g), log_G = 0;
   while ((1u << log_G) < g0) log_G++;
-  while (m > 1) {
+  while (m > 8) {
     // the block-wide level (k_reduce_block in msm.cu), its phases run thread by thread
     const uint32_t chunks = reduce_chunks(m);
     nxt.assign((size_t)g.sets * chunks, SR());
@@ -244,6 +244,11 @@ int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars,
     m = chunks;
     log_G += 10;
     cur.swap(nxt);
+  }
+  {  // the last <= 8 elements of every set: folded by the host code of msm.cu
+    std::vector<SR> fin(g.sets);
+    for (uint32_t s = 0; s < g.sets; s++) fin[s] = reduce_fold_final(cur.data() + (size_t)s * m, m, log_G);
+    cur.swap(fin);
   }
   std::vector<G1XYZZ> ws(g.sets);
   for (uint32_t s = 0; s < g.sets; s++) {

@@ -140,19 +140,34 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t* counts, uint32_t n
 }
 
 // sorted[offsets[key] + cursor++] = point index | sign << 31
+// A scalar's windows are handled eight at a time: all their cursor atomics are in flight together before the
+// first returned position is needed (the kernel is bound by the latency of those atomics, not by their number).
 __global__ void k_msm_scatter(ScalarBatch sb, uint64_t n, int from_mont, MsmGeom g, const uint32_t* offsets,
                               uint32_t* cursors, uint32_t* sorted) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t k = blockIdx.y;
   DigitWalk dw(sb.p[k], i, from_mont);
-  for (uint32_t w = 0; w < g.W; w++) {
-    uint32_t neg, d = dw.next(w, g, neg);
-    if (!d) continue;
-    const uint32_t key = msm_bucket_key(g, k, w, d);
-    if (key == 0xffffffffu) continue;
-    uint32_t pos = offsets[key] + atomicAdd(&cursors[key], 1u);
-    sorted[pos] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
+  for (uint32_t w0 = 0; w0 < g.W; w0 += 8) {
+    uint32_t key[8], val[8], pos[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      key[j] = 0xffffffffu;
+      const uint32_t w = w0 + j;
+      if (w < g.W) {
+        uint32_t neg, d = dw.next(w, g, neg);
+        if (d) {
+          key[j] = msm_bucket_key(g, k, w, d);
+          val[j] = (uint32_t)((uint64_t)w * g.point_stride + i) | (neg << 31);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (key[j] != 0xffffffffu) pos[j] = __ldg(offsets + key[j]) + atomicAdd(&cursors[key[j]], 1u);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (key[j] != 0xffffffffu) sorted[pos[j]] = val[j];
   }
 }
 
@@ -308,6 +323,7 @@ __global__ void __launch_bounds__(256) k_reduce_block(BlockLevelArgs a) {
   blk_local(a, set, chunk, t, s, x);
   sh[t] = s;
   __syncthreads();
+#pragma unroll 1
   for (uint32_t d = 1; d < 256; d <<= 1) {
     const G1XYZZ v = blk_scan_step(sh, t, d);
     __syncthreads();
@@ -319,6 +335,7 @@ __global__ void __launch_bounds__(256) k_reduce_block(BlockLevelArgs a) {
   __syncthreads();
   sh[t] = y;
   __syncthreads();
+#pragma unroll 1
   for (uint32_t d = 128; d > 0; d >>= 1) {
     blk_tree_step(sh, t, d);
     __syncthreads();
@@ -635,7 +652,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   uint32_t m = reduce_groups(ra.m, ra.g), log_G = log_g0;
   SR* cur = lvl_a.as<SR>();
   SR* nxt = lvl_b.as<SR>();
-  while (m > 1) {
+  while (m > 8) {  // the last few elements are folded on the host, which reads the result anyway
     BlockLevelArgs ba;
     ba.in = cur; ba.out = nxt; ba.sets = g.sets; ba.m = m; ba.log_G = log_G;
     k_reduce_block<<<dim3(reduce_chunks(m), g.sets), 256, 0, st>>>(ba);
@@ -646,24 +663,30 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   }
   ctx->time_end(3);
   PB_CUDA(cudaGetLastError());
+  // the remaining m (<= 8) elements per set are folded on the host (reduce_fold_final)
   std::vector<G1XYZZ> ws(g.sets);
   if (comm) {
     // the MSM join: one allgather of sets * 256 bytes per rank, then a few host additions (the commitment has to
     // reach the host for the Fiat-Shamir transcript anyway)
     const uint32_t world = (uint32_t)comm_world(comm);
     DevBuf& gath = ctx->msm_aff[2];
-    gath.ensure((size_t)world * g.sets * sizeof(SR));
+    const size_t per_rank = (size_t)g.sets * m;  // every rank has the same m
+    gath.ensure((size_t)world * per_rank * sizeof(SR));
     SR* all = gath.as<SR>();
-    PB_CUDA(cudaMemcpyAsync(all + (size_t)comm_rank(comm) * g.sets, cur, g.sets * sizeof(SR), cudaMemcpyDeviceToDevice, st));
-    comm_allgather_inplace(comm, all, g.sets * sizeof(SR), st);
-    std::vector<SR> fin((size_t)world * g.sets);
-    PB_CUDA(cudaMemcpyAsync(fin.data(), all, fin.size() * sizeof(SR), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(all + (size_t)comm_rank(comm) * per_rank, cur, per_rank * sizeof(SR), cudaMemcpyDeviceToDevice, st));
+    comm_allgather_inplace(comm, all, per_rank * sizeof(SR), st);
+    std::vector<SR> raw((size_t)world * per_rank), fin((size_t)world * g.sets);
+    PB_CUDA(cudaMemcpyAsync(raw.data(), all, raw.size() * sizeof(SR), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t rho = 0; rho < world; rho++)
+      for (uint32_t s = 0; s < g.sets; s++)
+        fin[(size_t)rho * g.sets + s] = reduce_fold_final(raw.data() + (size_t)rho * per_rank + (size_t)s * m, m, log_G);
     host_join_bucket_shards(fin.data(), world, g.sets, g.nloc, ws.data());
   } else {
-    std::vector<SR> fin(g.sets);
-    PB_CUDA(cudaMemcpyAsync(fin.data(), cur, g.sets * sizeof(SR), cudaMemcpyDeviceToHost, st));
+    std::vector<SR> raw((size_t)g.sets * m), fin(g.sets);
+    PB_CUDA(cudaMemcpyAsync(raw.data(), cur, raw.size() * sizeof(SR), cudaMemcpyDeviceToHost, st));
     PB_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t s = 0; s < g.sets; s++) fin[s] = reduce_fold_final(raw.data() + (size_t)s * m, m, log_G);
     // set result = sum_j (lo + j + 1) B_j = R + lo * S
     for (uint32_t s = 0; s < g.sets; s++) {
       ws[s] = fin[s].R;

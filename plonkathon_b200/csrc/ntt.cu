@@ -122,6 +122,22 @@ __device__ __forceinline__ void st_planes(uint4* lo, uint4* hi, uint32_t i, cons
   lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
   hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
+// Data-tile accessors with an XOR swizzle of the low three index bits (a 16-byte access is served per quarter
+// warp, 8 lanes x 16 B = one 128-byte wavefront when the 8 addresses differ in those bits).  Without it the
+// bit-reversed tile load (lanes differ only in high index bits) and the first register-blocked round (lanes 8
+// elements apart) put all 8 lanes of a wavefront on the same banks: ncu counted 3.5-4.7 M conflicts per pass.
+// XOR-ing bits 3..5 and the top three bits of the index into bits 0..2 makes every access pattern of the kernel
+// touch 8 distinct 16-byte columns; it is a bijection on the tile, so no padding is needed.
+struct TileSwz {
+  uint32_t top_shift, mask;  // mask = 7, or 0 for tiles too small to swizzle
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i ^ (((i >> 3) ^ (i >> top_shift)) & mask); }
+};
+__device__ __forceinline__ Fr ld_tile(const uint4* lo, const uint4* hi, uint32_t i, const TileSwz& z) {
+  return ld_planes(lo, hi, z(i));
+}
+__device__ __forceinline__ void st_tile(uint4* lo, uint4* hi, uint32_t i, const Fr& r, const TileSwz& z) {
+  st_planes(lo, hi, z(i), r);
+}
 __device__ __forceinline__ Fr ld_global(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
   uint4 a = __ldg(q), b = __ldg(q + 1);
@@ -173,12 +189,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 // j = (low t0 bits of base) + (k mod 2^s) * 2^t0.
 __device__ __forceinline__ void ntt_round8(uint4* s_lo, uint4* s_hi, const uint4* t_lo, const uint4* t_hi, uint32_t q,
                                            uint32_t c, uint32_t t0, uint32_t s_first, uint32_t log_b,
-                                           uint32_t log_cc) {
+                                           uint32_t log_cc, const TileSwz& z) {
   const uint32_t low = q & ((1u << t0) - 1);
   const uint32_t base = ((q >> t0) << (t0 + 3)) | low;
   Fr x[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) x[k] = ld_planes(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c);
+  for (int k = 0; k < 8; k++) x[k] = ld_tile(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c, z);
 #pragma unroll
   for (int s = 0; s < 3; s++) {
     if ((uint32_t)s < s_first) continue;
@@ -200,7 +216,7 @@ __device__ __forceinline__ void ntt_round8(uint4* s_lo, uint4* s_hi, const uint4
     }
   }
 #pragma unroll
-  for (int k = 0; k < 8; k++) st_planes(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c, x[k]);
+  for (int k = 0; k < 8; k++) st_tile(s_lo, s_hi, ((base + ((uint32_t)k << t0)) << log_cc) | c, x[k], z);
 }
 
 #ifndef PB_NTT_THREADS
@@ -217,6 +233,10 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
   uint4* t_hi = t_lo + TW;
   uint64_t* bar = reinterpret_cast<uint64_t*>(t_hi + TW);
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const uint32_t log_te = p.log_b + p.log_cc;
+  TileSwz z;
+  z.mask = log_te >= 6 ? 7u : 0u;
+  z.top_shift = log_te >= 6 ? log_te - 3 : 0;
 
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
       }
     }
     uint32_t br = p.log_b ? (__brev(b) >> (32 - p.log_b)) : 0;
-    st_planes(s_lo, s_hi, (br << p.log_cc) | c, x);
+    st_tile(s_lo, s_hi, (br << p.log_cc) | c, x, z);
   }
   __syncthreads();          // also orders tid 0's barrier init before the waits below
   mbar_wait(bar, 0);        // twiddles have landed
@@ -260,13 +280,13 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
     const uint32_t groups = TE >> 3;  // (B / 8) x CC threads' worth of work
     uint32_t t0 = 0;
     for (; t0 + 3 <= p.log_b; t0 += 3) {
-      for (uint32_t w = tid; w < groups; w += nth) ntt_round8(s_lo, s_hi, t_lo, t_hi, w >> p.log_cc, w & (CC - 1), t0, 0, p.log_b, p.log_cc);
+      for (uint32_t w = tid; w < groups; w += nth) ntt_round8(s_lo, s_hi, t_lo, t_hi, w >> p.log_cc, w & (CC - 1), t0, 0, p.log_b, p.log_cc, z);
       __syncthreads();
     }
     if (t0 < p.log_b) {
       const uint32_t rem = p.log_b - t0;  // 1 or 2 stages left: run them as the tail of a group at log_b - 3
       for (uint32_t w = tid; w < groups; w += nth)
-        ntt_round8(s_lo, s_hi, t_lo, t_hi, w >> p.log_cc, w & (CC - 1), p.log_b - 3, 3 - rem, p.log_b, p.log_cc);
+        ntt_round8(s_lo, s_hi, t_lo, t_hi, w >> p.log_cc, w & (CC - 1), p.log_b - 3, 3 - rem, p.log_b, p.log_cc, z);
       __syncthreads();
     }
   } else {
@@ -278,11 +298,11 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
         uint32_t j = qq & (half - 1), grp = qq >> t;
         uint32_t i0 = (((grp << (t + 1)) + j) << p.log_cc) | c;
         uint32_t i1 = i0 + (half << p.log_cc);
-        Fr u = ld_planes(s_lo, s_hi, i0);
-        Fr v = ld_planes(s_lo, s_hi, i1);
+        Fr u = ld_tile(s_lo, s_hi, i0, z);
+        Fr v = ld_tile(s_lo, s_hi, i1, z);
         if (t > 0) v = fp_mul(v, ld_planes(t_lo, t_hi, j << (p.log_b - 1 - t)));
-        st_planes(s_lo, s_hi, i0, fp_add(u, v));
-        st_planes(s_lo, s_hi, i1, fp_sub(u, v));
+        st_tile(s_lo, s_hi, i0, fp_add(u, v), z);
+        st_tile(s_lo, s_hi, i1, fp_sub(u, v), z);
       }
       __syncthreads();
     }
@@ -291,7 +311,7 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
   // ---- store (batch index fastest)
   for (uint32_t e = tid; e < TE; e += nth) {
     uint32_t c = e & (CC - 1), k = e >> p.log_cc;
-    Fr x = ld_planes(s_lo, s_hi, e);
+    Fr x = ld_tile(s_lo, s_hi, e, z);
     if (p.twg) x = fp_mul(x, ld_global(p.twg + gbase + (uint64_t)c * p.g_cs + (uint64_t)k * p.g_bs));
     if (p.has_final_scale) x = fp_mul(x, p.final_scale);
     uint64_t go = wbase + (uint64_t)c * p.w_cs + (uint64_t)k * p.w_bs;

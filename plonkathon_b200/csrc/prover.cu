@@ -494,11 +494,15 @@ static uint32_t read_flag(Prover* P, int idx) {
   return v;
 }
 
+Comm* ctx_comm(Context* ctx);
+
 // evaluate up to 8 coefficient-form polynomials (n coeffs each, Montgomery) at Montgomery points:
 // two strided-Horner levels on the device (n -> 4096 -> 32 partial values), the last 32 on the host
 static void eval_polys(Prover* P, int count, const Fr* const* polys, const Fr* xs, Fr* out) {
   Context* ctx = P->ctx;
-  const uint64_t n = P->n;
+  // one proof across G ranks: rank r evaluates the slab of coefficients [r n/G, (r+1) n/G) of every polynomial;
+  // the G partial values x^(r n/G) * slab(x) are exchanged with one small allgather and added on the host
+  const uint64_t n = P->n / (uint64_t)P->world, lo = n * (uint64_t)P->rank;
   uint32_t NC1 = (uint32_t)std::min<uint64_t>(n, 4096);
   uint32_t NC2 = std::min<uint32_t>(NC1, 32);
   ctx->scratch[0].ensure((size_t)count * (NC1 + NC2) * 32);
@@ -507,7 +511,7 @@ static void eval_polys(Prover* P, int count, const Fr* const* polys, const Fr* x
   EvalArgs a;
   a.n = n;
   a.NC = NC1;
-  for (int p = 0; p < count; p++) { a.poly[p] = polys[p]; a.x_nc[p] = fp_pow_u64(xs[p], NC1); }
+  for (int p = 0; p < count; p++) { a.poly[p] = polys[p] + lo; a.x_nc[p] = fp_pow_u64(xs[p], NC1); }
   k_horner_strided<<<dim3((NC1 + 127) / 128, count), 128, 0, ctx->stream>>>(a, H1);
   EvalArgs b;
   b.n = NC1;
@@ -521,7 +525,22 @@ static void eval_polys(Prover* P, int count, const Fr* const* polys, const Fr* x
   for (int p = 0; p < count; p++) {
     Fr acc = Fr::zero();
     for (uint32_t c = NC2; c-- > 0;) acc = fp_add(fp_mul(acc, xs[p]), h[(size_t)p * NC2 + c]);
-    out[p] = acc;
+    out[p] = P->world > 1 ? fp_mul(acc, fp_pow_u64(xs[p], lo)) : acc;
+  }
+  if (P->world > 1) {
+    const size_t bytes = (size_t)count * 32;
+    ctx->gather.ensure((size_t)P->world * bytes);
+    Fr* all = ctx->gather.as<Fr>();
+    PB_CUDA(cudaMemcpyAsync(all + (size_t)P->rank * count, out, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    comm_allgather_inplace(ctx_comm(ctx), all, bytes, ctx->stream);
+    std::vector<Fr> parts((size_t)P->world * count);
+    PB_CUDA(cudaMemcpyAsync(parts.data(), all, parts.size() * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < count; p++) {
+      Fr acc = Fr::zero();
+      for (int r = 0; r < P->world; r++) acc = fp_add(acc, parts[(size_t)r * count + p]);
+      out[p] = acc;
+    }
   }
 }
 
@@ -580,12 +599,17 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     }
     PB_CUDA(cudaEventRecord(ctx->copy_done[3], st));  // the destination buffers are free once prior work is done
     PB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[3], 0));
+    // one proof across G ranks: every rank stages only its 1/G slab of each wire column over PCIe and the ranks
+    // exchange slabs over NVLink (one allgather per column) -- the host is read once, not G times
+    const uint64_t slab = n / (uint64_t)P->world, first = slab * (uint64_t)P->rank;
     for (int k = 0; k < 3; k++) {
-      PB_CUDA(cudaMemcpyAsync(P->lag[k].p, src[k], n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+      PB_CUDA(cudaMemcpyAsync(P->lag[k].as<Fr>() + first, src[k] + first * 32, slab * 32, cudaMemcpyHostToDevice,
+                              ctx->copy_stream));
       PB_CUDA(cudaEventRecord(ctx->copy_done[k], ctx->copy_stream));
     }
     for (int k = 0; k < 3; k++) {
       PB_CUDA(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
+      if (P->world > 1) comm_allgather_inplace(ctx_comm(ctx), P->lag[k].p, slab * 32, st);
       fr_to_mont(ctx, P->lag[k].as<Fr>(), P->lag[k].as<Fr>(), n);
       if (P->world == 1) ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
     }

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from .curve import Scalar
-from .field import CURVE_ORDER, FQ
+from .field import CURVE_ORDER, FIELD_MODULUS, FQ
 from .poly import Basis, _log2_exact, scalars_to_bytes
 from .transcript import Message1, Message2, Message3, Message4, Message5, Transcript
 
@@ -52,8 +52,13 @@ class Proof:
 
     @classmethod
     def from_bytes(cls, raw: bytes) -> "Proof":
+        """Inverse of to_bytes.  The encoding is canonical: coordinates must be below q and evaluations below r
+        (ValueError otherwise) -- a second byte string for the same proof would make proofs malleable."""
         assert len(raw) == 768
         w = [int.from_bytes(raw[i:i + 32], "big") for i in range(0, 768, 32)]
+        for k, x in enumerate(w):
+            if x >= (CURVE_ORDER if 14 <= k < 20 else FIELD_MODULUS):
+                raise ValueError("non-canonical proof encoding (word %d is not reduced)" % k)
         pt = lambda k: (FQ(w[k]), FQ(w[k + 1]))  # noqa: E731
         return cls(Message1(pt(0), pt(2), pt(4)), Message2(pt(6)), Message3(pt(8), pt(10), pt(12)),
                    Message4(*[Scalar(x) for x in w[14:20]]), Message5(pt(20), pt(22)))

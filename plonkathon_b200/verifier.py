@@ -13,7 +13,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 
 from .curve import G1, G2, Scalar, ec_lincomb, g1_neg, g2_add, g2_mul, pairing_product_is_one
-from .field import CURVE_ORDER
+from . import _lib
+from .field import CURVE_ORDER, FIELD_MODULUS
 from .transcript import Transcript
 
 
@@ -54,9 +55,30 @@ class VerificationKey:
         pi_ev = _lagrange_terms_at(group_order, [-int(x) % CURVE_ORDER for x in public], zeta)
         return beta, gamma, alpha, zeta, v, u, proof, zh_ev, l0_ev, pi_ev
 
+    @staticmethod
+    def _well_formed(pf) -> bool:
+        """every commitment of the proof is a point of the curve y^2 = x^3 + 3 with reduced coordinates and every
+        evaluation is a reduced scalar: a malformed proof is rejected (False), it must not reach the MSM"""
+        for v in pf.flatten().values():
+            if isinstance(v, tuple):
+                x, y = int(v[0]), int(v[1])
+                if not (0 <= x < FIELD_MODULUS and 0 <= y < FIELD_MODULUS and (y * y - x * x * x - 3) % FIELD_MODULUS == 0):
+                    return False
+            elif v is None or not 0 <= int(v) < CURVE_ORDER:
+                return False
+        return True
+
     def verify_proof(self, group_order: int, pf, public=[]) -> bool:
         """verifier.py:40-73: the batched form -- one pairing equation, the linearisation commitment never
-        formed on its own."""
+        formed on its own.  Malformed proofs (points off the curve, the identity) are rejected, not raised."""
+        if not self._well_formed(pf):
+            return False
+        try:
+            return self._verify_batched(group_order, pf, public)
+        except _lib.PlonkB200Error:
+            return False
+
+    def _verify_batched(self, group_order: int, pf, public) -> bool:
         beta, gamma, alpha, zeta, v, u, proof, zh_ev, l0_ev, pi_ev = self._common(group_order, pf, public)
         a, b, c = proof["a_eval"], proof["b_eval"], proof["c_eval"]
         s1, s2, zw = proof["s1_eval"], proof["s2_eval"], proof["z_shifted_eval"]
@@ -85,6 +107,14 @@ class VerificationKey:
     def verify_proof_unoptimized(self, group_order: int, pf, public=[]) -> bool:
         """verifier.py:76-92: rebuild the commitment to the prover's linearisation polynomial R (R(zeta) == 0),
         then check the opening at zeta and the opening of Z at zeta*w separately."""
+        if not self._well_formed(pf):
+            return False
+        try:
+            return self._verify_unoptimized(group_order, pf, public)
+        except _lib.PlonkB200Error:
+            return False
+
+    def _verify_unoptimized(self, group_order: int, pf, public) -> bool:
         beta, gamma, alpha, zeta, v, u, proof, zh_ev, l0_ev, pi_ev = self._common(group_order, pf, public)
         a, b, c = proof["a_eval"], proof["b_eval"], proof["c_eval"]
         s1, s2, zw = proof["s1_eval"], proof["s2_eval"], proof["z_shifted_eval"]

@@ -794,7 +794,7 @@ def test_polynomial_ring_ops_on_device(pb):
     L, M = pb.Basis.LAGRANGE, pb.Basis.MONOMIAL
 
     def resident(v, basis):  # a Polynomial whose data lives in HBM only (the result of a transform)
-        p = pb.Polynomial(S(pb, v), L if basis == M else M)
+        p = pb.Polynomial(S(pb, v), basis)
         q = p.ifft().fft() if basis == L else p.fft().ifft()  # round trip: same values, device-resident
         assert q._values is None and q.on_device and q.basis == basis
         return q

@@ -131,6 +131,21 @@ def test_verifier_accepts_golden_and_rejects_tampered(name, monkeypatch):
     bad = raw[:k] + ((int.from_bytes(raw[k:k + 32], "big") + 5) % R).to_bytes(32, "big") + raw[k + 32:]
     assert not vk.verify_proof(n, pb.Proof.from_bytes(bad), public)
     assert not vk.verify_proof_unoptimized(n, pb.Proof.from_bytes(bad), public)
+    # malformed proofs are rejected, not raised: a commitment that is not on the curve ...
+    k = 32 * 1  # y of a_1
+    bad = raw[:k] + ((int.from_bytes(raw[k:k + 32], "big") + 1) % O.Q_MOD).to_bytes(32, "big") + raw[k + 32:]
+    assert not vk.verify_proof(n, pb.Proof.from_bytes(bad), public)
+    assert not vk.verify_proof_unoptimized(n, pb.Proof.from_bytes(bad), public)
+    # ... and the encoding is canonical: the same proof with x + q or an evaluation + r does not decode
+    x0 = int.from_bytes(raw[:32], "big")
+    if x0 + O.Q_MOD < 1 << 256:
+        with pytest.raises(ValueError):
+            pb.Proof.from_bytes((x0 + O.Q_MOD).to_bytes(32, "big") + raw[32:])
+    k = 32 * 14
+    e0 = int.from_bytes(raw[k:k + 32], "big")
+    if e0 + R < 1 << 256:
+        with pytest.raises(ValueError):
+            pb.Proof.from_bytes(raw[:k] + (e0 + R).to_bytes(32, "big") + raw[k + 32:])
 
 
 def test_pairing_entry_point_edge_cases():
