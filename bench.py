@@ -513,12 +513,13 @@ def b200_arm(args):
         # BASELINE.json configs[3]: a full Prover.prove at the size of test/mini_poseidon (n = 1024), host buffers
         small = syn.build_circuit(10, seed=args.seed, n_public=2)
         spk, sA, sB, sC, spub = syn.circuit_arrays(small)
-        sprover = pb.Prover.from_arrays(setup, 1 << 10, spk)
+        ssetup = pb.Setup.generate(TAU, 1 << 10, ctx=ctx)  # its own 2^10-power SRS (window table sized for 1024 points)
+        sprover = pb.Prover.from_arrays(ssetup, 1 << 10, spk)
         sprover.prove_arrays(sA, sB, sC, spub)
         ms = timed_local(torch, stream, lambda: sprover.prove_arrays(sA, sB, sC, spub), 10) / 10
         comp["prove_2^10_gates_latency"] = {"ms": ms, "proofs_per_s": 1e3 / ms,
                                             "note": "one proof at a time, host buffers, rounds 1-5 + transcript"}
-        del sprover
+        del sprover, ssetup
         if shard is not None:
             one_ms = ms_solo / args.steps
             base_ntt = comp["fr_ntt_fwd_plus_inv_2^%d" % log_n]["ms"]

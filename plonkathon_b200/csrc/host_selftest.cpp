@@ -3,7 +3,6 @@
 // tests/test_host_arith.py through ctypes; never linked into libplonk_b200.so.
 #include "field.cuh"
 #include "curve.cuh"
-#include "fieldd.cuh"
 #include "msm_digits.cuh"
 #include "modinv.cuh"
 #include "msm_bucket.cuh"
@@ -63,13 +62,6 @@ int hs_msm_digits(const uint32_t* scalar, uint32_t c, int32_t* digits, uint32_t*
   }
   *n_windows = g.W;
   return (int)dw.carry;
-}
-
-// FP64-pipe multiplier: out = a * b * 2^-260 mod p on plain integers a, b < p (8 x u32 limbs in and out)
-int hs_fieldd_mul(int field, const uint32_t* a, const uint32_t* b, uint32_t* out) {
-  if (field == 0) { Fr r = fpd_to_u32(fpd_mul(fpd_from_u32(ld<Fr>(a)), fpd_from_u32(ld<Fr>(b)))); st(out, r); }
-  else { Fq r = fpd_to_u32(fpd_mul(fpd_from_u32(ld<Fq>(a)), fpd_from_u32(ld<Fq>(b)))); st(out, r); }
-  return 0;
 }
 
 // G1 ops on Montgomery-form coordinates.  xyzz: 4x8 limbs (X, Y, ZZ, ZZZ); affine: 2x8 limbs + inf flag.
@@ -227,22 +219,23 @@ int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars,
     ba.in = cur.data(); ba.out = nxt.data(); ba.sets = g.sets; ba.m = m; ba.log_G = log_G;
     for (uint32_t set = 0; set < g.sets; set++)
       for (uint32_t chunk = 0; chunk < chunks; chunk++) {
-        std::vector<G1XYZZ> sh(256), xs(256), tmp(256);
-        for (uint32_t t = 0; t < 256; t++) blk_local(ba, set, chunk, t, sh[t], xs[t]);
-        for (uint32_t d = 1; d < 256; d <<= 1) {
-          for (uint32_t t = 0; t < 256; t++) tmp[t] = blk_scan_step(sh.data(), t, d);
+        const uint32_t NT = PB_REDUCE_THREADS;
+        std::vector<G1XYZZ> sh(NT), xs(NT), tmp(NT);
+        for (uint32_t t = 0; t < NT; t++) blk_local(ba, set, chunk, t, sh[t], xs[t]);
+        for (uint32_t d = 1; d < NT; d <<= 1) {
+          for (uint32_t t = 0; t < NT; t++) tmp[t] = blk_scan_step(sh.data(), t, d);
           sh = tmp;
         }
         const G1XYZZ s_total = sh[0];
-        for (uint32_t t = 0; t < 256; t++) tmp[t] = blk_weight(ba, t, xs[t], sh[t]);
+        for (uint32_t t = 0; t < NT; t++) tmp[t] = blk_weight(ba, t, xs[t], sh[t]);
         sh = tmp;
-        for (uint32_t d = 128; d > 0; d >>= 1)
-          for (uint32_t t = 0; t < 256; t++) blk_tree_step(sh.data(), t, d);
+        for (uint32_t d = NT / 2; d > 0; d >>= 1)
+          for (uint32_t t = 0; t < NT; t++) blk_tree_step(sh.data(), t, d);
         nxt[(size_t)set * chunks + chunk].S = s_total;
         nxt[(size_t)set * chunks + chunk].R = sh[0];
       }
     m = chunks;
-    log_G += 10;
+    log_G += 9;
     cur.swap(nxt);
   }
   {  // the last <= 8 elements of every set: folded by the host code of msm.cu

@@ -316,15 +316,15 @@ __global__ void __launch_bounds__(128) k_msm_stitch_heavy(const G1XYZZ* slots, c
 __global__ void __launch_bounds__(128) k_reduce_level0(ReduceArgs a) {
   reduce_level0_thread(a, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
 }
-__global__ void __launch_bounds__(256) k_reduce_block(BlockLevelArgs a) {
-  __shared__ G1XYZZ sh[256];
+__global__ void __launch_bounds__(PB_REDUCE_THREADS) k_reduce_block(BlockLevelArgs a) {
+  __shared__ G1XYZZ sh[PB_REDUCE_THREADS];
   const uint32_t t = threadIdx.x, chunk = blockIdx.x, set = blockIdx.y;
   G1XYZZ s, x;
   blk_local(a, set, chunk, t, s, x);
   sh[t] = s;
   __syncthreads();
 #pragma unroll 1
-  for (uint32_t d = 1; d < 256; d <<= 1) {
+  for (uint32_t d = 1; d < PB_REDUCE_THREADS; d <<= 1) {
     const G1XYZZ v = blk_scan_step(sh, t, d);
     __syncthreads();
     sh[t] = v;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) k_reduce_block(BlockLevelArgs a) {
   sh[t] = y;
   __syncthreads();
 #pragma unroll 1
-  for (uint32_t d = 128; d > 0; d >>= 1) {
+  for (uint32_t d = PB_REDUCE_THREADS / 2; d > 0; d >>= 1) {
     blk_tree_step(sh, t, d);
     __syncthreads();
   }
@@ -655,10 +655,10 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   while (m > 8) {  // the last few elements are folded on the host, which reads the result anyway
     BlockLevelArgs ba;
     ba.in = cur; ba.out = nxt; ba.sets = g.sets; ba.m = m; ba.log_G = log_G;
-    k_reduce_block<<<dim3(reduce_chunks(m), g.sets), 256, 0, st>>>(ba);
+    k_reduce_block<<<dim3(reduce_chunks(m), g.sets), PB_REDUCE_THREADS, 0, st>>>(ba);
     ctx->launches++;
     m = reduce_chunks(m);
-    log_G += 10;
+    log_G += 9;  // log2(PB_REDUCE_CHUNK)
     std::swap(cur, nxt);
   }
   ctx->time_end(3);

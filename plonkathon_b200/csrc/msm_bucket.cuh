@@ -350,10 +350,10 @@ PB_HD void reduce_level0_thread(const ReduceArgs& a, uint64_t t) {
   a.out[t] = o;
 }
 
-// ---- levels >= 1: one block of 256 threads folds a chunk of 1024 elements ------------------------------------
+// ---- levels >= 1: one block of 128 threads folds a chunk of 512 elements --------------------------------------
 // Above level 0 there are too few elements to fill the machine, so a level is bound by the length of its chains of
-// dependent additions, not by throughput: a block-wide suffix scan and a tree keep that length at ~25 additions for
-// a group of 1024 (a thread-per-group level of 16 has 48, and four times as many levels).
+// dependent additions, not by throughput: a block-wide suffix scan and a tree keep that length at ~23 additions for
+// a group of 512 (a thread-per-group level of 16 has 48, and more than twice as many levels).
 //   element index in the chunk: lo = 4 t + e, e < 4;   S' = sum S,   R' = G sum_lo lo S_lo + sum R
 //   thread t: s_t = sum_e S, w_t = sum_e e S_e, r_t = sum_e R  ->  x_t = r_t + G w_t
 //   suffix scan: suf_t = sum_{t' >= t} s_t'                     ->  S' = suf_0, sum_t t s_t = sum_{t >= 1} suf_t
@@ -369,7 +369,11 @@ inline void blk_add(G1XYZZ& acc, const G1XYZZ& q) { g1_add(acc, q); }
 inline void blk_double(G1XYZZ& a) { g1_double(a); }
 #endif
 
-#define PB_REDUCE_CHUNK 1024
+// 128 threads = one warp per SM sub-partition: the integer pipe of a sub-partition serves one dependent chain at
+// full speed, two warps on it would each run their chain at half speed (measured: 256-thread blocks took ~10 us per
+// addition, twice the single-warp latency)
+#define PB_REDUCE_THREADS 128
+#define PB_REDUCE_CHUNK (4 * PB_REDUCE_THREADS)
 struct BlockLevelArgs {
   const SR* in;
   SR* out;
@@ -399,7 +403,7 @@ PB_HD void blk_local(const BlockLevelArgs& a, uint32_t set, uint32_t chunk, uint
 // one Hillis-Steele step of the inclusive suffix scan: value of position t after combining with t + d
 PB_HD G1XYZZ blk_scan_step(const G1XYZZ* sh, uint32_t t, uint32_t d) {
   G1XYZZ v = sh[t];
-  if (t + d < 256) {
+  if (t + d < PB_REDUCE_THREADS) {
     const G1XYZZ o = sh[t + d];
     blk_add(v, o);
   }

@@ -75,17 +75,20 @@ class Polynomial:
         return self._dev is not None
 
     def _device(self, ctx):
-        """canonical [n, 32] uint8 CUDA tensor holding the values, on the context's device (uploaded once)"""
+        """canonical [n, 32] uint8 CUDA tensor holding the values, on the context's device.  A device-born polynomial
+        hands out its HBM copy; a list-backed one is uploaded on every call -- the list is the source of truth and
+        may have been edited in place since the last call (the reference's semantics)."""
         import torch
         dev = torch.device("cuda", ctx.device)
-        if self._dev is not None and self._dev.device != dev:
-            self._dev = self._dev.to(dev)
-        if self._dev is None:
-            raw = bytearray(scalars_to_bytes(self._values))
-            t = torch.frombuffer(raw, dtype=torch.uint8).reshape(-1, 32) if raw else torch.empty((0, 32), dtype=torch.uint8)
-            self._dev = t.to(dev)
-            torch.cuda.current_stream(dev).synchronize()  # the library runs on its own stream
-        return self._dev
+        if self._dev is not None:
+            if self._dev.device != dev:
+                self._dev = self._dev.to(dev)
+            return self._dev
+        raw = bytearray(scalars_to_bytes(self._values))
+        t = torch.frombuffer(raw, dtype=torch.uint8).reshape(-1, 32) if raw else torch.empty((0, 32), dtype=torch.uint8)
+        t = t.to(dev)
+        torch.cuda.current_stream(dev).synchronize()  # the library runs on its own stream
+        return t
 
     def __eq__(self, other):
         if self.basis != other.basis:

@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(ROOT, "build", "host_selftest.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(CSRC, "host_selftest.cpp")
-    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "fieldd.cuh", "msm_digits.cuh", "msm_bucket.cuh", "modinv.cuh")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "msm_digits.cuh", "msm_bucket.cuh", "modinv.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
                                "-I", CSRC, "-o", out])
@@ -130,20 +130,6 @@ def test_curve_ops(lib):
         o5 = (ctypes.c_uint32 * 32)()
         lib.hs_curve_op(2, o3, limbs(0, 4), 0, o5)
         assert to_affine(lib, o5) == to_affine(lib, o4)
-
-
-@pytest.mark.parametrize("field,p", [(0, O.R_MOD), (1, O.Q_MOD)])
-def test_fp64_pipe_multiplier(lib, field, p):
-    """csrc/fieldd.cuh: the DFMA-based Montgomery product (52-bit limbs in doubles, radix 2^260), host-emulated"""
-    rng = random.Random(10 + field)
-    r260_inv = pow(1 << 260, -1, p)
-    vals = EDGE + [p - 1, p - 2, (1 << 52) - 1, (1 << 104) - 1, ((1 << 52) - 1) << 52, (1 << 253) + 12345] + \
-        [rng.randrange(p) for _ in range(300)]
-    for i, a in enumerate(vals):
-        b = vals[(i * 5 + 1) % len(vals)]
-        out = (ctypes.c_uint32 * 8)()
-        assert lib.hs_fieldd_mul(field, limbs(a), limbs(b), out) == 0
-        assert unlimbs(out) == a * b * r260_inv % p, (hex(a), hex(b))
 
 
 def test_msm_signed_digit_slicing(lib):
