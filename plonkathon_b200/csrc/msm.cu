@@ -652,7 +652,10 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   uint32_t m = reduce_groups(ra.m, ra.g), log_G = log_g0;
   SR* cur = lvl_a.as<SR>();
   SR* nxt = lvl_b.as<SR>();
-  while (m > 8) {  // the last few elements are folded on the host, which reads the result anyway
+  // the last few elements are folded on the host, which reads the result anyway; with a communicator every rank
+  // reduces to ONE pair per set first, so the host join stays at world * sets additions
+  const uint32_t m_stop = comm ? 1 : 8;
+  while (m > m_stop) {
     BlockLevelArgs ba;
     ba.in = cur; ba.out = nxt; ba.sets = g.sets; ba.m = m; ba.log_G = log_G;
     k_reduce_block<<<dim3(reduce_chunks(m), g.sets), PB_REDUCE_THREADS, 0, st>>>(ba);
