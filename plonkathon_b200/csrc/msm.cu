@@ -609,7 +609,19 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     DevBuf& buckets = ctx->scratch[5];
     DevBuf& seg = ctx->scratch[1];
     buckets.ensure((size_t)g.nb * sizeof(G1XYZZ));
-    const uint32_t L = env_u32("PB200_MSM_SEG", 32);
+    // entries per thread: 32 when there is plenty of work; a rank that owns a small share of the buckets (or a small
+    // MSM) takes shorter segments so that the launch still has ~2 threads per resident slot -- its time is then the
+    // length of one thread's chain of dependent additions, not throughput
+    static const uint32_t seg_env = env_u32("PB200_MSM_SEG", 0);
+    uint32_t L = 32;
+    if (seg_env) {
+      L = seg_env;
+    } else {
+      const uint64_t expected = entries / (g.half / g.nloc);  // digits are close to uniform over the buckets
+      while (L > 4 && expected / L < (uint64_t)ctx->sm_count * 1024) L >>= 1;
+      // the per-segment scratch is sized for the worst case (all entries owned): keep it below 1 GiB
+      while (L < 32 && (entries / L) * (2 * sizeof(G1XYZZ) + 12 + sizeof(HeavyItem)) > (1ull << 30)) L <<= 1;
+    }
     PB_CHECK(L >= 1 && L <= 4096, "bad PB200_MSM_SEG");
     const uint32_t n_seg = (uint32_t)((entries + L - 1) / L);
     seg.ensure((size_t)n_seg * 2 * sizeof(G1XYZZ) + (size_t)n_seg * 3 * 4 + (size_t)n_seg * sizeof(HeavyItem) + 16);
@@ -633,10 +645,16 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   }
 
   // bucket reduction: levels of grouped running sums until one (S, R) pair per set is left
-  static const uint32_t g0_env = env_u32("PB200_MSM_G", 16);
+  // level-0 group size: 16 buckets per thread when that still fills the machine, down to 4 for small bucket counts
+  // (a sharded rank, a small MSM), where the level is bound by the length of a thread's chain instead
+  static const uint32_t g0_env = env_u32("PB200_MSM_G", 0);
   uint32_t log_g0 = 4;
-  while ((1u << log_g0) < g0_env && log_g0 < 10) log_g0++;
-  if ((1u << log_g0) > g0_env && log_g0 > 1) log_g0--;
+  if (g0_env) {
+    log_g0 = 1;
+    while ((2u << log_g0) <= g0_env && log_g0 < 10) log_g0++;
+  } else {
+    while (log_g0 > 2 && (g.nb >> log_g0) < (uint32_t)ctx->sm_count * 256) log_g0--;
+  }
   ctx->time_begin(3);
   ra.sets = g.sets;
   ra.m = g.nloc;

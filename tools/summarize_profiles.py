@@ -17,7 +17,7 @@ import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 launches = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/%s_launches.csv" % tag
-capture = sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/%s_full.ncu-rep" % tag
+capture = sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/%s_full_raw.csv" % tag  # ncu -i <rep> --page raw --csv
 os.makedirs("profiles", exist_ok=True)
 
 # ---- launch list
@@ -61,7 +61,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 if os.path.exists(capture):
-    out = subprocess.run(["ncu", "-i", capture, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if capture.endswith(".ncu-rep"):
+        out = subprocess.run(["ncu", "-i", capture, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        out = open(capture).read()
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     kn, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
