@@ -191,7 +191,9 @@ int pb200_srs_commit_partial(pb200_ctx* ctx, pb200_srs* srs, const void* d_coeff
 int pb200_srs_bucket_count(pb200_srs* srs, uint32_t* out);
 int pb200_g1_combine_partials_host(const uint8_t* h_xyzz, unsigned count, uint8_t* h_out_xy, int* is_identity);
 /* the host half of the sharded commitment's join: h_sr = [world][sets] pairs (S = sum of the rank's buckets,
- * R = sum_j (j+1) B_j over them; 2 x 128 bytes XYZZ); rank rho owns buckets [rho * nloc, (rho+1) * nloc) */
+ * R = sum_j (j+1) B_j over them, j the rank's local bucket index; 2 x 128 bytes XYZZ).  nloc > 0: rank rho owns the
+ * contiguous buckets [rho * nloc, (rho+1) * nloc); nloc == 0: strided ownership, rank rho owns the buckets
+ * world * k + rho (what pb200_srs_commit_coeffs_sharded uses: skewed digits spread over all ranks). */
 int pb200_g1_join_bucket_shards_host(const uint8_t* h_sr, unsigned world, unsigned sets, uint32_t nloc, uint8_t* h_out_xy,
                                      int* is_identity);
 

@@ -53,6 +53,7 @@ void prover_round5(Prover* P, const Fr& v_c);
 void prover_serialize(const Prover* P, uint8_t* out768);
 void g1_combine_partials_host(const G1XYZZ* parts, uint32_t count, uint8_t* out_xy, int* is_identity);
 void host_join_bucket_shards(const SR* all, uint32_t world, uint32_t sets, uint32_t nloc, G1XYZZ* out);
+void host_join_bucket_shards_strided(const SR* all, uint32_t world, uint32_t sets, G1XYZZ* out);
 }  // namespace pb200
 
 using namespace pb200;
@@ -534,7 +535,8 @@ int pb200_g1_join_bucket_shards_host(const uint8_t* h_sr, unsigned world, unsign
   std::vector<SR> all((size_t)world * sets);
   memcpy(all.data(), h_sr, all.size() * sizeof(SR));
   std::vector<G1XYZZ> ws(sets);
-  host_join_bucket_shards(all.data(), world, sets, nloc, ws.data());
+  if (nloc == 0) host_join_bucket_shards_strided(all.data(), world, sets, ws.data());
+  else host_join_bucket_shards(all.data(), world, sets, nloc, ws.data());
   for (unsigned k = 0; k < sets; k++) g1_combine_partials_host(&ws[k], 1, h_out_xy + 64 * k, is_identity + k);
   PB_API_END
 }

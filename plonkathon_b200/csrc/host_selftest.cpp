@@ -52,6 +52,8 @@ int hs_msm_digits(const uint32_t* scalar, uint32_t c, int32_t* digits, uint32_t*
   g.batch = 1;
   g.lo = 0;
   g.nloc = g.half;
+  g.own_log = 0;
+  g.own_rank = 0;
   g.sets = g.W;
   g.nb = g.half * g.W;
   Fr s = ld<Fr>(scalar);
@@ -127,10 +129,20 @@ int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars,
   g.fixed_base = fixed_base ? 1 : 0;
   g.point_stride = fixed_base ? n : 0;
   g.batch = batch;
-  if (hi > g.half) hi = g.half;
-  if (lo >= hi) return -1;
-  g.lo = lo;
-  g.nloc = hi - lo;
+  g.own_log = 0;
+  g.own_rank = 0;
+  if (hi >= 0xfffffff0u && hi != 0xffffffffu) {  // strided shard: 2^(0xffffffff - hi) ranks, rank = lo
+    g.own_log = 0xffffffffu - hi;
+    g.own_rank = lo;
+    g.lo = 0;
+    g.nloc = g.half >> g.own_log;
+    if (!g.nloc || lo >= (1u << g.own_log)) return -1;
+  } else {
+    if (hi > g.half) hi = g.half;
+    if (lo >= hi) return -1;
+    g.lo = lo;
+    g.nloc = hi - lo;
+  }
   g.sets = fixed_base ? batch : g.W;
   g.nb = g.sets * g.nloc;
   // point table
@@ -245,6 +257,19 @@ int hs_msm_pipeline(const uint32_t* points, uint32_t n, const uint32_t* scalars,
   }
   std::vector<G1XYZZ> ws(g.sets);
   for (uint32_t s = 0; s < g.sets; s++) {
+    if (g.own_log) {  // strided shard: sum_k (G k + r + 1) B_k = G R + (r + 1 - G) S
+      std::vector<SR> one(1, cur[s]);
+      // a one-rank "join" with the rank's own coefficient: reuse the library's formula through its pieces
+      G1XYZZ gr = cur[s].R;
+      for (uint32_t k = 0; k < g.own_log; k++) g1_double(gr);
+      G1XYZZ ms = G1XYZZ::identity();
+      const uint32_t coef = (1u << g.own_log) - 1 - g.own_rank;  // subtract (G - 1 - r) S
+      for (int i = 31; i >= 0; i--) { g1_double(ms); if ((coef >> i) & 1) g1_add(ms, cur[s].S); }
+      ms.Y = fp_neg(ms.Y);
+      g1_add(gr, ms);
+      ws[s] = gr;
+      continue;
+    }
     ws[s] = cur[s].R;
     G1XYZZ ml = G1XYZZ::identity();
     for (int i = 31; i >= 0; i--) { g1_double(ml); if ((g.lo >> i) & 1) g1_add(ml, cur[s].S); }

@@ -256,14 +256,17 @@ __global__ void __launch_bounds__(128) k_msm_seg_accumulate(const G1Affine* poin
   }
 }
 
-struct HeavyItem { uint32_t bucket, own_slot, t0, t1; };
+struct HeavyItem { uint32_t bucket, own_slot, t0, t1, piece_base, pieces; };
+struct HeavyPiece { uint32_t item, index; };
+#define PB_STITCH_PIECE 1024  // segments per piece of a very heavy bucket (a short top window puts n / 4 entries in one)
 
-// one thread per segment: if it owns a boundary-crossing bucket, stitch it (or queue it as heavy)
+// one thread per segment: if it owns a boundary-crossing bucket, stitch it (or queue it as heavy; a bucket that
+// spans more than PB_STITCH_PIECE segments is also cut into pieces that k_msm_stitch_pieces sums block by block)
 __global__ void __launch_bounds__(128) k_msm_stitch(const uint32_t* offsets, uint32_t nb, uint32_t L,
                                                     uint32_t n_segments, const G1XYZZ* slots,
                                                     const uint32_t* slot_bucket, const uint32_t* own_slot,
                                                     G1XYZZ* buckets, HeavyItem* heavy, uint32_t* heavy_count,
-                                                    uint32_t small_limit) {
+                                                    HeavyPiece* pieces, uint32_t small_limit) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_segments) return;
   const uint32_t os = own_slot[t];
@@ -272,7 +275,12 @@ __global__ void __launch_bounds__(128) k_msm_stitch(const uint32_t* offsets, uin
   const uint32_t t1 = (offsets[b + 1] - 1) / L;  // last segment the bucket reaches
   if (t1 - t > small_limit) {
     uint32_t h = atomicAdd(heavy_count, 1u);
-    HeavyItem it; it.bucket = b; it.own_slot = os; it.t0 = t; it.t1 = t1;
+    HeavyItem it; it.bucket = b; it.own_slot = os; it.t0 = t; it.t1 = t1; it.piece_base = 0; it.pieces = 0;
+    if (t1 - t > PB_STITCH_PIECE) {
+      it.pieces = (t1 - t + PB_STITCH_PIECE - 1) / PB_STITCH_PIECE;
+      it.piece_base = atomicAdd(heavy_count + 1, it.pieces);
+      for (uint32_t p = 0; p < it.pieces; p++) { HeavyPiece hp; hp.item = h; hp.index = p; pieces[it.piece_base + p] = hp; }
+    }
     heavy[h] = it;
     return;
   }
@@ -284,29 +292,65 @@ __global__ void __launch_bounds__(128) k_msm_stitch(const uint32_t* offsets, uin
   buckets[b] = acc;
 }
 
+// block-wide sum of one G1XYZZ per thread (128 threads); result in sh[0]
+__device__ __forceinline__ void block_sum_xyzz(G1XYZZ* sh, const G1XYZZ& mine) {
+  sh[threadIdx.x] = mine;
+  __syncthreads();
+  for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
+    if (threadIdx.x < d) {
+      G1XYZZ a = sh[threadIdx.x], c = sh[threadIdx.x + d];
+      g1_add(a, c);
+      sh[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// pieces of very heavy buckets: one block each (grid-stride over the piece list): partial[p] = sum of the first-run
+// slots of the piece's segments
+__global__ void __launch_bounds__(128) k_msm_stitch_pieces(const G1XYZZ* slots, const HeavyItem* heavy,
+                                                           const uint32_t* heavy_count, const HeavyPiece* pieces,
+                                                           G1XYZZ* partial) {
+  __shared__ G1XYZZ sh[128];
+  const uint32_t count = heavy_count[1];
+  for (uint32_t p = blockIdx.x; p < count; p += gridDim.x) {
+    const HeavyPiece hp = pieces[p];
+    const HeavyItem it = heavy[hp.item];
+    const uint32_t lo = it.t0 + 1 + hp.index * PB_STITCH_PIECE;
+    const uint32_t hi = min(lo + PB_STITCH_PIECE - 1, it.t1);
+    G1XYZZ acc = G1XYZZ::identity();
+    for (uint32_t k = lo + threadIdx.x; k <= hi; k += blockDim.x) {
+      G1XYZZ piece = slots[2 * k];
+      g1_add(acc, piece);
+    }
+    block_sum_xyzz(sh, acc);
+    if (threadIdx.x == 0) partial[p] = sh[0];
+    __syncthreads();
+  }
+}
+
 // heavy buckets: one block each (grid-stride over the queue), strided partial sums + shared-memory tree
 __global__ void __launch_bounds__(128) k_msm_stitch_heavy(const G1XYZZ* slots, const HeavyItem* heavy,
-                                                          const uint32_t* heavy_count, G1XYZZ* buckets) {
+                                                          const uint32_t* heavy_count, const G1XYZZ* partial,
+                                                          G1XYZZ* buckets) {
   __shared__ G1XYZZ sh[128];
   const uint32_t count = *heavy_count;
   for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
     HeavyItem it = heavy[h];
     G1XYZZ acc = G1XYZZ::identity();
     if (threadIdx.x == 0) acc = slots[it.own_slot];
-    for (uint32_t k = it.t0 + 1 + threadIdx.x; k <= it.t1; k += blockDim.x) {
-      G1XYZZ piece = slots[2 * k];
-      g1_add(acc, piece);
-    }
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (uint32_t d = blockDim.x >> 1; d > 0; d >>= 1) {
-      if (threadIdx.x < d) {
-        G1XYZZ a = sh[threadIdx.x], c = sh[threadIdx.x + d];
-        g1_add(a, c);
-        sh[threadIdx.x] = a;
+    if (it.pieces) {
+      for (uint32_t p = threadIdx.x; p < it.pieces; p += blockDim.x) {
+        G1XYZZ piece = partial[it.piece_base + p];
+        g1_add(acc, piece);
       }
-      __syncthreads();
+    } else {
+      for (uint32_t k = it.t0 + 1 + threadIdx.x; k <= it.t1; k += blockDim.x) {
+        G1XYZZ piece = slots[2 * k];
+        g1_add(acc, piece);
+      }
     }
+    block_sum_xyzz(sh, acc);
     if (threadIdx.x == 0) buckets[it.bucket] = sh[0];
     __syncthreads();
   }
@@ -478,6 +522,29 @@ static uint32_t pick_B(Context* ctx, uint64_t slots, uint32_t r) {
 
 // sum over ranks rho of (R_rho + rho * nloc * S_rho) for every bucket set: the partial sums of equal bucket ranges
 // [rho * nloc, (rho + 1) * nloc), nloc a power of two.  all: [world][sets] (S, R) pairs.
+// The same join for STRIDED shards (rank rho owns the buckets j = G k + rho; what the communicator path uses):
+// sum_k (G k + rho + 1) B = G R_rho + (rho + 1 - G) S_rho, so the total is G sum R_rho - sum (G - 1 - rho) S_rho.
+void host_join_bucket_shards_strided(const SR* all, uint32_t world, uint32_t sets, G1XYZZ* out) {
+  uint32_t log_g = 0;
+  while ((1u << log_g) < world) log_g++;
+  PB_CHECK((1u << log_g) == world, "strided bucket shards need a power-of-two rank count");
+  for (uint32_t s = 0; s < sets; s++) {
+    G1XYZZ run = G1XYZZ::identity(), weighted = G1XYZZ::identity(), plain = G1XYZZ::identity();
+    for (uint32_t rho = 0; rho < world; rho++) {
+      const SR& e = all[(size_t)rho * sets + s];
+      g1_add(plain, e.R);
+      if (rho + 1 < world) {
+        g1_add(run, e.S);       // sum_{rho' <= rho} S
+        g1_add(weighted, run);  // -> sum (G - 1 - rho) S_rho
+      }
+    }
+    for (uint32_t k = 0; k < log_g; k++) g1_double(plain);
+    weighted.Y = fp_neg(weighted.Y);
+    g1_add(plain, weighted);
+    out[s] = plain;
+  }
+}
+
 void host_join_bucket_shards(const SR* all, uint32_t world, uint32_t sets, uint32_t nloc, G1XYZZ* out) {
   uint32_t log_nloc = 0;
   while ((1u << log_nloc) < nloc) log_nloc++;
@@ -516,11 +583,16 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
   g.fixed_base = fixed_base ? 1 : 0;
   g.point_stride = fixed_base ? point_stride : 0;
   g.batch = batch;
+  g.own_log = 0;
+  g.own_rank = 0;
   if (comm && comm_world(comm) > 1) {
-    const uint32_t per = g.half >> comm_log_world(comm);
-    PB_CHECK(per >= 1, "more ranks than buckets");
-    bucket_lo = per * (uint32_t)comm_rank(comm);
-    bucket_hi = bucket_lo + per;
+    // strided ownership: rank r takes the buckets j = G k + r, so the few buckets a short top window (or a skewed
+    // witness) concentrates on are spread over all ranks
+    PB_CHECK((g.half >> comm_log_world(comm)) >= 1, "more ranks than buckets");
+    g.own_log = (uint32_t)comm_log_world(comm);
+    g.own_rank = (uint32_t)comm_rank(comm);
+    bucket_lo = 0;
+    bucket_hi = g.half >> g.own_log;
   } else {
     comm = nullptr;
   }
@@ -618,18 +690,22 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
       L = seg_env;
     } else {
       const uint64_t expected = entries / (g.half / g.nloc);  // digits are close to uniform over the buckets
-      while (L > 4 && expected / L < (uint64_t)ctx->sm_count * 1024) L >>= 1;
+      while (L > 4 && expected / L < (uint64_t)ctx->sm_count * 256) L >>= 1;  // 256 threads saturate an SM's multiplier
       // the per-segment scratch is sized for the worst case (all entries owned): keep it below 1 GiB
       while (L < 32 && (entries / L) * (2 * sizeof(G1XYZZ) + 12 + sizeof(HeavyItem)) > (1ull << 30)) L <<= 1;
     }
     PB_CHECK(L >= 1 && L <= 4096, "bad PB200_MSM_SEG");
     const uint32_t n_seg = (uint32_t)((entries + L - 1) / L);
-    seg.ensure((size_t)n_seg * 2 * sizeof(G1XYZZ) + (size_t)n_seg * 3 * 4 + (size_t)n_seg * sizeof(HeavyItem) + 16);
+    const uint32_t max_pieces = 2 * (n_seg / PB_STITCH_PIECE) + 16;
+    seg.ensure((size_t)n_seg * 2 * sizeof(G1XYZZ) + (size_t)n_seg * 3 * 4 + (size_t)n_seg * sizeof(HeavyItem) + 16 +
+               (size_t)max_pieces * (sizeof(HeavyPiece) + sizeof(G1XYZZ)));
     G1XYZZ* slots = seg.as<G1XYZZ>();
-    uint32_t* slot_bucket = reinterpret_cast<uint32_t*>(slots + (size_t)n_seg * 2);
+    G1XYZZ* piece_partial = slots + (size_t)n_seg * 2;
+    uint32_t* slot_bucket = reinterpret_cast<uint32_t*>(piece_partial + max_pieces);
     uint32_t* own_slot = slot_bucket + (size_t)n_seg * 2;
-    uint32_t* heavy_count = own_slot + n_seg;
+    uint32_t* heavy_count = own_slot + n_seg;  // [0] heavy items, [1] pieces
     HeavyItem* heavy = reinterpret_cast<HeavyItem*>(heavy_count + 4);
+    HeavyPiece* pieces = reinterpret_cast<HeavyPiece*>(heavy + n_seg);
     PB_CUDA(cudaMemsetAsync(buckets.p, 0, (size_t)g.nb * sizeof(G1XYZZ), st));
     PB_CUDA(cudaMemsetAsync(own_slot, 0xff, (size_t)n_seg * 4, st));
     PB_CUDA(cudaMemsetAsync(heavy_count, 0, 16, st));
@@ -638,8 +714,10 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
                                                              g.nb, L, buckets.as<G1XYZZ>(), slots, slot_bucket, own_slot);
     ctx->time_end(0);
     k_msm_stitch<<<(n_seg + 127) / 128, 128, 0, st>>>(offsets.as<uint32_t>(), g.nb, L, n_seg, slots, slot_bucket,
-                                                     own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, 16);
-    k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, buckets.as<G1XYZZ>());
+                                                     own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, pieces, 16);
+    k_msm_stitch_pieces<<<std::min<uint32_t>(max_pieces, 592), 128, 0, st>>>(slots, heavy, heavy_count, pieces, piece_partial);
+    k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, piece_partial, buckets.as<G1XYZZ>());
+    ctx->launches += 1;
     ctx->launches += 3;
     ra.xb = buckets.as<G1XYZZ>();
   }
@@ -702,7 +780,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     for (uint32_t rho = 0; rho < world; rho++)
       for (uint32_t s = 0; s < g.sets; s++)
         fin[(size_t)rho * g.sets + s] = reduce_fold_final(raw.data() + (size_t)rho * per_rank + (size_t)s * m, m, log_G);
-    host_join_bucket_shards(fin.data(), world, g.sets, g.nloc, ws.data());
+    host_join_bucket_shards_strided(fin.data(), world, g.sets, ws.data());
   } else {
     std::vector<SR> raw((size_t)g.sets * m), fin(g.sets);
     PB_CUDA(cudaMemcpyAsync(raw.data(), cur, raw.size() * sizeof(SR), cudaMemcpyDeviceToHost, st));

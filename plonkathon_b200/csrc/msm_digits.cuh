@@ -11,15 +11,24 @@ struct MsmGeom {
   uint32_t fixed_base;      // 1: one bucket set per batched scalar vector, shared by all windows; 0: one per window
   uint64_t point_stride;    // generic: 0 ; fixed-base: n (index of window w's copy of point i = w*n + i)
   uint32_t batch;           // fixed-base only: number of MSMs sharing the points
-  uint32_t lo, nloc;        // this launch owns bucket magnitudes d with lo <= d - 1 < lo + nloc (bucket-range shard)
+  uint32_t lo, nloc;        // this launch owns bucket magnitudes d with lo <= d - 1 < lo + nloc (bucket-range shard) ...
+  uint32_t own_log, own_rank;  // ... or, when own_log > 0, every 2^own_log-th bucket: (d - 1) mod 2^own_log == own_rank,
+                               // local index (d - 1) >> own_log, nloc = half >> own_log (strided shard: the buckets
+                               // that skewed digits concentrate on -- the short top window -- spread over all ranks)
   uint32_t sets;            // bucket sets: fixed-base: batch ; generic: W
   uint32_t nb;              // sets * nloc local buckets
 };
 
 // local bucket of digit magnitude d >= 1 of window w of scalar vector k, or 0xffffffff when another rank owns it
 PB_HD uint32_t msm_bucket_key(const MsmGeom& g, uint32_t k, uint32_t w, uint32_t d) {
-  const uint32_t j = d - 1 - g.lo;  // wraps for d - 1 < lo
-  if (j >= g.nloc) return 0xffffffffu;
+  uint32_t j;
+  if (g.own_log) {
+    if (((d - 1) & ((1u << g.own_log) - 1)) != g.own_rank) return 0xffffffffu;
+    j = (d - 1) >> g.own_log;
+  } else {
+    j = d - 1 - g.lo;  // wraps for d - 1 < lo
+    if (j >= g.nloc) return 0xffffffffu;
+  }
   return (g.fixed_base ? k : w) * g.nloc + j;
 }
 

@@ -51,7 +51,8 @@ def combine_partials(parts: bytes, count: int):
 
 def join_bucket_shards(sr: bytes, world: int, sets: int, nloc: int):
     """Host half of the sharded commitment's join: `sr` = [world][sets] (S, R) pairs of 2 x 128 bytes; returns a list
-    of (x||y bytes, is_identity) per set."""
+    of (x||y bytes, is_identity) per set.  nloc > 0: contiguous bucket ranges of that width; nloc == 0: strided
+    ownership (rank rho owns the buckets world * k + rho), the layout the library's sharded commitments use."""
     out = ctypes.create_string_buffer(64 * sets)
     ident = (ctypes.c_int * sets)()
     _lib.check(_lib.lib().pb200_g1_join_bucket_shards_host(sr, world, sets, nloc, out, ident))

@@ -218,6 +218,14 @@ def test_msm_bucket_pipeline_on_host(lib):
     sc = rand()
     got, _ = _msm_pipeline(lib, points, [sc], 13, False, 0, 1 << 30, 16, 2)
     assert got[0] == _oracle_msm(points, sc)
+    # strided shards (what the communicator path uses: rank r owns the buckets G k + r, so the buckets a short top
+    # window concentrates on spread over all ranks): the partial sums G R + (r + 1 - G) S add up to the full result
+    for log_g in (1, 2, 3):
+        acc = [None] * len(vecs)
+        for r in range(1 << log_g):
+            part, _ = _msm_pipeline(lib, points, vecs, 5, True, r, 0xFFFFFFFF - log_g, 4, 2)
+            acc = [O.g1_add(a, p) for a, p in zip(acc, part)]
+        assert acc == expect, log_g
     # an empty result: all scalars zero
     got, _ = _msm_pipeline(lib, points, [[0] * n], 4, False, 0, 1 << 30, 4, 4)
     assert got == [None]

@@ -153,15 +153,20 @@ def _bucket_join_worker(rank, world, port, q):
             elif d:
                 buckets[d - 1] = O.g1_add(buckets[d - 1], cur)
             cur = O.g1_multiply(cur, 1 << c)
+    want = O.ec_lincomb_naive(list(zip(pts, sc)))
+    ok = True
     lo, hi = parallel.bucket_range(half, rank, world)
-    S = R = None
-    for j, b in enumerate(buckets[lo:hi]):
-        S = O.g1_add(S, b)
-        R = O.g1_add(R, O.g1_multiply(b, j + 1) if b else None)
-    gathered = parallel.allgather_bytes(_xyzz_bytes(S) + _xyzz_bytes(R))
-    (xy, ident), = parallel.join_bucket_shards(b"".join(gathered), world, 1, hi - lo)
-    got = None if ident else (int.from_bytes(xy[:32], "little"), int.from_bytes(xy[32:], "little"))
-    q.put((rank, got == O.ec_lincomb_naive(list(zip(pts, sc)))))
+    # contiguous ranges (operator level) and strided ownership (the library's sharded commitments): local bucket j
+    for own, nloc in ((buckets[lo:hi], hi - lo), (buckets[rank::world], 0)):
+        S = R = None
+        for j, b in enumerate(own):
+            S = O.g1_add(S, b)
+            R = O.g1_add(R, O.g1_multiply(b, j + 1) if b else None)
+        gathered = parallel.allgather_bytes(_xyzz_bytes(S) + _xyzz_bytes(R))
+        (xy, ident), = parallel.join_bucket_shards(b"".join(gathered), world, 1, nloc)
+        got = None if ident else (int.from_bytes(xy[:32], "little"), int.from_bytes(xy[32:], "little"))
+        ok = ok and got == want
+    q.put((rank, ok))
     dist.barrier()
     dist.destroy_process_group()
 

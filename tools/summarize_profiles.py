@@ -85,8 +85,8 @@ if os.path.exists(capture):
                 if h in WANT:
                     f.write("| %s | %s | %s |\n" % (h, u, v))
             f.write("\n")
-    # the dominant kernel's DRAM traffic per point for bench.py (largest k_msm_seg_accumulate launch = a batch of 3
-    # commitments of 2^20 points)
+    # the dominant kernel's DRAM traffic per point for bench.py (the largest captured k_msm_seg_accumulate launch: a
+    # batch of 1-3 commitments of 2^20 points; the point count follows from its grid)
     if "k_msm_seg_accumulate" in best:
         r = best["k_msm_seg_accumulate"][1]
 
@@ -96,7 +96,7 @@ if os.path.exists(capture):
             return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
         dram = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
         grid = float(r[hdr.index("launch__grid_size")].replace(",", ""))
-        points = 3 * (1 << 20)
+        points = grid * 128 * 32 / 13.0  # 128 threads per block, 32 sorted entries per thread, 13 windows per point
         json.dump({"kernel": "k_msm_seg_accumulate", "log_n": 20, "points_in_captured_launch": points,
                    "grid_size": grid, "dram_bytes_in_captured_launch": dram, "dram_bytes_per_point": dram / points,
                    "source": capture}, open("profiles/%s_dominant_kernel.json" % tag, "w"), indent=1)
