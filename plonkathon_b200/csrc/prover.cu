@@ -198,18 +198,35 @@ __global__ void __launch_bounds__(256) k_prod_scan_tiles(Fr* tile_prod, uint32_t
   }
   if (threadIdx.x == 0) *total_out = total;
 }
-__global__ void __launch_bounds__(256) k_prod_apply(const Fr* f, uint64_t n, const Fr* tile_prod, Fr* Z) {
+// carry (optional): the product of everything below this vector (the slabs of the lower ranks in a sharded round 2)
+__global__ void __launch_bounds__(256) k_prod_apply(const Fr* f, uint64_t n, const Fr* tile_prod, const Fr* carry, Fr* Z) {
   __shared__ Fr sh[256];
   uint64_t base = (uint64_t)blockIdx.x * PB_PROD_TILE + threadIdx.x * 8;
   Fr c[8];
   Fr p = Fr::one();
   for (int k = 0; k < 8; k++) { c[k] = base + k < n ? ldg_fr(f + base + k) : Fr::one(); p = fp_mul(p, c[k]); }
   Fr total;
-  Fr run = fp_mul(tile_prod[blockIdx.x], block_exclusive_prod_256(p, sh, &total));
+  Fr start = tile_prod[blockIdx.x];
+  if (carry) start = fp_mul(start, ldg_fr(carry));
+  Fr run = fp_mul(start, block_exclusive_prod_256(p, sh, &total));
   for (int k = 0; k < 8; k++) {
     if (base + k < n) Z[base + k] = run;
     run = fp_mul(run, c[k]);
   }
+}
+
+// sharded grand product: totals[r] = product of slab r (gathered).  carry = product of the slabs below `rank`,
+// grand = product of all of them (Z_n, which must be 1: prover.py:132)
+__global__ void k_prod_carry(const Fr* totals, uint32_t world, uint32_t rank, Fr* carry, Fr* grand) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr c = Fr::one(), all = Fr::one();
+  for (uint32_t r = 0; r < world; r++) {
+    Fr t = totals[r];
+    if (r < rank) c = fp_mul(c, t);
+    all = fp_mul(all, t);
+  }
+  *carry = c;
+  *grand = all;
 }
 
 // ---- division by (X - z) in coefficient space ---------------------------------------------------------------
@@ -257,9 +274,11 @@ __global__ void __launch_bounds__(256) k_sufsum_scan_tiles(Fr* tile_sum, uint32_
   }
   if (threadIdx.x == 0) *total_out = total;
 }
-// out[m-1] = z^-m * sum_(m' >= m) N_m' z^m'  for m >= 1 ; out[n-1] = 0 ; the m = 0 sum (== N(z)) is dropped
+// out[m-1] = z^-m * (carry + sum_(m' >= m) N_m' z^m')  for m >= 1 ; out[n-1] = carry * z^-n ; the m = 0 sum is dropped.
+// One device: carry = 0 (the m = 0 sum is N(z), the remainder).  Slab of a sharded division: N, zpow, zinvpow and out
+// point at the slab, `carry` holds the sums of the slabs above it and last_scale = z^-(first index above the slab).
 __global__ void __launch_bounds__(256) k_sufsum_apply(const Fr* N, const Fr* zpow, const Fr* zinvpow, uint64_t n,
-                                                      const Fr* tile_sum, Fr* out) {
+                                                      const Fr* tile_sum, const Fr* carry, Fr last_scale, Fr* out) {
   __shared__ Fr sh[256];
   uint64_t base = (uint64_t)blockIdx.x * PB_SUM_TILE + threadIdx.x * 8;
   Fr c[8];
@@ -269,8 +288,9 @@ __global__ void __launch_bounds__(256) k_sufsum_apply(const Fr* N, const Fr* zpo
     else c[k] = Fr::zero();
     p = fp_add(p, c[k]);
   }
+  const Fr cy = carry ? ldg_fr(carry) : Fr::zero();
   Fr total;
-  Fr run = fp_add(tile_sum[blockIdx.x], block_exclusive_sum_256(p, sh, &total));
+  Fr run = fp_add(fp_add(tile_sum[blockIdx.x], cy), block_exclusive_sum_256(p, sh, &total));
   for (int k = 0; k < 8; k++) {
     run = fp_add(run, c[k]);  // inclusive suffix sum at m
     if (base + k < n) {
@@ -278,7 +298,21 @@ __global__ void __launch_bounds__(256) k_sufsum_apply(const Fr* N, const Fr* zpo
       if (m >= 1) out[m - 1] = fp_mul(run, ldg_fr(zinvpow + m));
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = Fr::zero();
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = fp_mul(cy, last_scale);
+}
+
+// sharded division: totals[r] = sum of slab r (gathered from all ranks).  carry = sum of the slabs above `rank`;
+// the grand total is the remainder N(z), which must vanish
+__global__ void k_sufsum_carry(const Fr* totals, uint32_t world, uint32_t rank, Fr* carry, uint32_t* nonzero) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr c = Fr::zero(), all = Fr::zero();
+  for (uint32_t r = 0; r < world; r++) {
+    Fr t = totals[r];
+    all = fp_add(all, t);
+    if (r > rank) c = fp_add(c, t);
+  }
+  *carry = c;
+  if (!all.is_zero()) atomicAdd(nonzero, 1u);
 }
 
 // basis_i[j] = w^i * (x_j^n - 1) / (n (x_j - w^i)) : the i-th Lagrange basis polynomial on the coset
@@ -353,10 +387,12 @@ __global__ void __launch_bounds__(128) k_horner_strided(EvalArgs a, Fr* H) {
 }
 
 // ---- coefficient-space linear combination: out[k] = sum_i w[i] * vec[i][k] (+ c0 at k == 0) -----------------
-struct LinCombArgs { const Fr* vec[16]; Fr w[16]; Fr c0; int count; uint64_t n; };
+// indices [first, first + n) of the result (a slab of a sharded round 5; first = 0, n = everything on one device)
+struct LinCombArgs { const Fr* vec[16]; Fr w[16]; Fr c0; int count; uint64_t n, first; };
 __global__ void __launch_bounds__(128) k_lincomb(LinCombArgs a, Fr* out) {
   uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.n) return;
+  k += a.first;
   Fr acc = k == 0 ? a.c0 : Fr::zero();
   for (int i = 0; i < a.count; i++) acc = fp_add(acc, fp_mul(a.w[i], ldg_fr(a.vec[i] + k)));
   out[k] = acc;
@@ -662,23 +698,40 @@ void prover_round2(Prover* P, const Fr& beta_c, const Fr& gamma_c) {
   P->beta = fp_to_mont(beta_c);
   P->gamma = fp_to_mont(gamma_c);
   PermChallenges ch{P->beta, P->gamma};
-  Fr* num = P->tmp[0].as<Fr>();
-  Fr* den = P->tmp[1].as<Fr>();
-  k_perm_terms<<<PB_GRID(n, 128), 0, st>>>(P->lag[0].as<Fr>(), P->lag[1].as<Fr>(), P->lag[2].as<Fr>(),
-                                          P->sel_lag[Prover::S1].as<Fr>(), P->sel_lag[Prover::S2].as<Fr>(),
-                                          P->sel_lag[Prover::S3].as<Fr>(), P->roots.as<Fr>(), ch, n, num, den);
-  uint64_t T = (n + PB_BATCH_CH - 1) / PB_BATCH_CH;
-  k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den, num, n, T);
-  uint32_t n_tiles = (uint32_t)((n + PB_PROD_TILE - 1) / PB_PROD_TILE);
+  // one proof across G ranks: rank r builds the slab [r n/G, (r+1) n/G) of the grand product -- per-row terms, the
+  // batched inversion and the in-slab prefix products are local; the slab products are exchanged with a 32-byte
+  // allgather (the product of the lower slabs is the slab's carry) and the Z values with one bulk allgather
+  const uint64_t ns = n / (uint64_t)P->world, lo = ns * (uint64_t)P->rank;
+  Fr* num = P->tmp[0].as<Fr>() + lo;
+  Fr* den = P->tmp[1].as<Fr>() + lo;
+  k_perm_terms<<<PB_GRID(ns, 128), 0, st>>>(P->lag[0].as<Fr>() + lo, P->lag[1].as<Fr>() + lo, P->lag[2].as<Fr>() + lo,
+                                           P->sel_lag[Prover::S1].as<Fr>() + lo, P->sel_lag[Prover::S2].as<Fr>() + lo,
+                                           P->sel_lag[Prover::S3].as<Fr>() + lo, P->roots.as<Fr>() + lo, ch, ns, num, den);
+  uint64_t T = (ns + PB_BATCH_CH - 1) / PB_BATCH_CH;
+  k_batch_div<<<PB_GRID(T, 128), 0, st>>>(num, den, num, ns, T);
+  uint32_t n_tiles = (uint32_t)((ns + PB_PROD_TILE - 1) / PB_PROD_TILE);
   PB_CHECK(n_tiles <= 65536, "group order too large for the product scan");
-  ctx->scratch[0].ensure((size_t)(n_tiles + 1) * 32);
+  ctx->scratch[0].ensure((size_t)(n_tiles + 1 + 16) * 32);
   Fr* tiles = ctx->scratch[0].as<Fr>();
-  k_prod_tiles<<<n_tiles, 256, 0, st>>>(num, n, tiles);
+  Fr* totals = tiles + n_tiles + 1;  // [world] slab products, then carry and grand total
+  k_prod_tiles<<<n_tiles, 256, 0, st>>>(num, ns, tiles);
   k_prod_scan_tiles<<<1, 256, 0, st>>>(tiles, n_tiles, tiles + n_tiles);
-  k_prod_apply<<<n_tiles, 256, 0, st>>>(num, n, tiles, P->lag[3].as<Fr>());
+  const Fr* d_total = tiles + n_tiles;
+  if (P->world > 1) {
+    PB_CUDA(cudaMemcpyAsync(totals + P->rank, tiles + n_tiles, 32, cudaMemcpyDeviceToDevice, st));
+    comm_allgather_inplace(ctx_comm(ctx), totals, 32, st);
+    Fr* carry = totals + P->world;
+    k_prod_carry<<<1, 32, 0, st>>>(totals, (uint32_t)P->world, (uint32_t)P->rank, carry, carry + 1);
+    k_prod_apply<<<n_tiles, 256, 0, st>>>(num, ns, tiles, carry, P->lag[3].as<Fr>() + lo);
+    comm_allgather_inplace(ctx_comm(ctx), P->lag[3].p, ns * 32, st);
+    d_total = carry + 1;
+    ctx->launches++;
+  } else {
+    k_prod_apply<<<n_tiles, 256, 0, st>>>(num, ns, tiles, nullptr, P->lag[3].as<Fr>());
+  }
   ctx->launches += 5;
   Fr total;
-  PB_CUDA(cudaMemcpyAsync(&total, tiles + n_tiles, 32, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaMemcpyAsync(&total, d_total, 32, cudaMemcpyDeviceToHost, st));
   {
     const Fr* zl = P->lag[3].as<Fr>();
     Fr* zc = P->coeff[3].as<Fr>();
@@ -782,19 +835,35 @@ void prover_round4(Prover* P, const Fr& zeta_c) {
 }
 
 // (num coefficients, n) / (X - point) -> quotient coefficients (out != num), remainder dropped.
-// Coefficient-space synthetic division as a weighted suffix sum (see k_sufsum_*).
+// Coefficient-space synthetic division as a weighted suffix sum (see k_sufsum_*).  One proof across G ranks: rank r
+// divides the slab of coefficients [r n/G, (r+1) n/G) -- `num` needs to be valid on that slab only --; the slab sums
+// are exchanged with a 32-byte allgather (the sums of the slabs above are the slab's carry), the quotient slabs with
+// one bulk allgather, so every rank ends up with the full quotient for its share of the commitment.
 static void divide_linear(Prover* P, const Fr* num, Fr* out, const Fr& point, Fr* pow_buf, Fr* invpow_buf) {
   Context* ctx = P->ctx;
-  const uint64_t n = P->n;
+  const uint64_t n = P->n / (uint64_t)P->world, lo = n * (uint64_t)P->rank;
   cudaStream_t st = ctx->stream;
-  launch_powers(ctx, pow_buf, n, point, Fr::one());
-  launch_powers(ctx, invpow_buf, n, fp_inv(point), Fr::one());
+  const Fr point_inv = fp_inv(point);
+  launch_powers(ctx, pow_buf + lo, n, point, fp_pow_u64(point, lo));
+  launch_powers(ctx, invpow_buf + lo, n, point_inv, fp_pow_u64(point_inv, lo));
   uint32_t n_tiles = (uint32_t)((n + PB_SUM_TILE - 1) / PB_SUM_TILE);
-  ctx->scratch[0].ensure((size_t)(n_tiles + 1) * 32);
+  ctx->scratch[0].ensure((size_t)(n_tiles + 1 + 16) * 32);
   Fr* tiles = ctx->scratch[0].as<Fr>();
-  k_sufsum_tiles<<<n_tiles, 256, 0, st>>>(num, pow_buf, n, tiles);
+  Fr* totals = tiles + n_tiles + 1;  // [world] slab sums, then the carry
+  k_sufsum_tiles<<<n_tiles, 256, 0, st>>>(num + lo, pow_buf + lo, n, tiles);
   k_sufsum_scan_tiles<<<1, 256, 0, st>>>(tiles, n_tiles, tiles + n_tiles);
-  k_sufsum_apply<<<n_tiles, 256, 0, st>>>(num, pow_buf, invpow_buf, n, tiles, out);
+  if (P->world > 1) {
+    PB_CUDA(cudaMemcpyAsync(totals + P->rank, tiles + n_tiles, 32, cudaMemcpyDeviceToDevice, st));
+    comm_allgather_inplace(ctx_comm(ctx), totals, 32, st);
+    Fr* carry = totals + P->world;
+    k_sufsum_carry<<<1, 32, 0, st>>>(totals, (uint32_t)P->world, (uint32_t)P->rank, carry, P->flags.as<uint32_t>());
+    k_sufsum_apply<<<n_tiles, 256, 0, st>>>(num + lo, pow_buf + lo, invpow_buf + lo, n, tiles, carry,
+                                           fp_pow_u64(point_inv, lo + n), out + lo);
+    comm_allgather_inplace(ctx_comm(ctx), out, n * 32, st);
+    ctx->launches += 5;
+    return;
+  }
+  k_sufsum_apply<<<n_tiles, 256, 0, st>>>(num, pow_buf, invpow_buf, n, tiles, nullptr, Fr::zero(), out);
   // the grand total is the remainder num(point); it must vanish (prover.py:267 R(zeta) == 0 and the degree
   // asserts of prover.py:288,299 are equivalent to exact divisibility)
   k_count_nonzero<<<1, 32, 0, st>>>(tiles + n_tiles, 1, P->flags.as<uint32_t>());
@@ -839,7 +908,8 @@ void prover_round5(Prover* P, const Fr& v_c) {
   add(P->sel_coeff[Prover::S1].as<Fr>(), v4);
   add(P->sel_coeff[Prover::S2].as<Fr>(), v5);
   L.count = k;
-  L.n = n;
+  L.n = n / (uint64_t)P->world;          // one proof across G ranks: every rank builds (and divides) its slab only
+  L.first = L.n * (uint64_t)P->rank;
   // constant term: PI(zeta) - c2 (c + gamma) - alpha^2 L0(zeta) - v a - v^2 b - v^3 c - v^4 s1 - v^5 s2
   Fr c0 = fp_sub(P->pi_ev, fp_mul(c2, fp_add(c, ga)));
   c0 = fp_sub(c0, al2l0);
@@ -851,15 +921,16 @@ void prover_round5(Prover* P, const Fr& v_c) {
   L.c0 = c0;
   Fr* wz = P->tmp[0].as<Fr>();
   PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
-  k_lincomb<<<PB_GRID(n, 128), 0, st>>>(L, wz);
+  k_lincomb<<<PB_GRID(L.n, 128), 0, st>>>(L, wz);
   ctx->launches++;
   Fr* wz_q = P->tmp[1].as<Fr>();
   divide_linear(P, wz, wz_q, zeta, P->tmp[2].as<Fr>(), P->tmp[3].as<Fr>());
   // W_zw numerator = Z - z_shifted_eval
   LinCombArgs M;
-  M.vec[0] = P->coeff[3].as<Fr>(); M.w[0] = one; M.count = 1; M.n = n; M.c0 = fp_neg(zw);
+  M.vec[0] = P->coeff[3].as<Fr>(); M.w[0] = one; M.count = 1; M.c0 = fp_neg(zw);
+  M.n = L.n; M.first = L.first;
   Fr* wzw = P->tmp[0].as<Fr>();  // the W_z numerator is no longer needed
-  k_lincomb<<<PB_GRID(n, 128), 0, st>>>(M, wzw);
+  k_lincomb<<<PB_GRID(M.n, 128), 0, st>>>(M, wzw);
   ctx->launches++;
   Fr* wzw_q = P->tmp[4].as<Fr>();
   divide_linear(P, wzw, wzw_q, fp_mul(zeta, fr_root_of_unity(P->log_n)), P->tmp[2].as<Fr>(), P->tmp[3].as<Fr>());

@@ -92,3 +92,54 @@ def test_small_dft_butterflies_match_definition(world):
                 u = y[i + j]
                 y[i + j], y[i + j + half] = (u + v) % P, (u - v) % P
     assert y == [sum(x[r] * pow(w, r * k, P) for r in range(world)) % P for k in range(world)]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_sharded_division_and_grand_product(world):
+    """Rounds 2 and 5 across ranks (csrc/prover.cu, world > 1).  Division by (X - z) in coefficient space is a weighted
+    suffix sum q_(k-1) = z^-k sum_(m >= k) N_m z^m: a rank handles a slab of m, its carry is the sum of the slabs
+    above, the top element of its output slab is carry * z^-(hi).  The grand product Z_(i+1) = Z_i f_i is an exclusive
+    prefix product: a rank's carry is the product of the slabs below."""
+    rng = random.Random(31 * world)
+    n = 32
+    z = rng.randrange(2, P)
+    q = [rng.randrange(P) for _ in range(n - 1)]           # quotient, degree n - 2
+    N = [0] * n                                             # N = q * (X - z): exactly divisible
+    for i, c in enumerate(q):
+        N[i + 1] = (N[i + 1] + c) % P
+        N[i] = (N[i] - c * z) % P
+    zinv = pow(z, -1, P)
+    ns = n // world
+    u = [N[m] * pow(z, m, P) % P for m in range(n)]
+    totals = [sum(u[r * ns:(r + 1) * ns]) % P for r in range(world)]
+    assert sum(totals) % P == 0                             # the remainder N(z)
+    out = [None] * n
+    for r in range(world):
+        lo, hi = r * ns, (r + 1) * ns
+        carry = sum(totals[r + 1:]) % P
+        run = carry
+        for m in range(hi - 1, lo - 1, -1):                 # k_sufsum_apply on the slab, from the top
+            run = (run + u[m]) % P
+            if m - lo >= 1:
+                out[m - 1] = run * pow(zinv, m, P) % P
+        out[hi - 1] = carry * pow(zinv, hi, P) % P
+    assert out == q + [0]
+    f = [rng.randrange(1, P) for _ in range(n)]
+    Z = [1]
+    for x in f[:-1]:
+        Z.append(Z[-1] * x % P)
+    prods = []
+    for r in range(world):
+        t = 1
+        for x in f[r * ns:(r + 1) * ns]:
+            t = t * x % P
+        prods.append(t)
+    got = []
+    for r in range(world):
+        run = 1
+        for t in prods[:r]:
+            run = run * t % P                               # k_prod_carry
+        for x in f[r * ns:(r + 1) * ns]:                    # k_prod_apply: exclusive prefix inside the slab
+            got.append(run)
+            run = run * x % P
+    assert got == Z
