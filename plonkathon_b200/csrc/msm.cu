@@ -589,10 +589,17 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     // strided ownership: rank r takes the buckets j = G k + r, so the few buckets a short top window (or a skewed
     // witness) concentrates on are spread over all ranks
     PB_CHECK((g.half >> comm_log_world(comm)) >= 1, "more ranks than buckets");
-    g.own_log = (uint32_t)comm_log_world(comm);
-    g.own_rank = (uint32_t)comm_rank(comm);
-    bucket_lo = 0;
-    bucket_hi = g.half >> g.own_log;
+    static const bool contiguous = getenv("PB200_SHARD_CONTIGUOUS") != nullptr;  // A/B switch: r * nloc .. (r+1) * nloc
+    if (contiguous) {
+      const uint32_t per = g.half >> comm_log_world(comm);
+      bucket_lo = per * (uint32_t)comm_rank(comm);
+      bucket_hi = bucket_lo + per;
+    } else {
+      g.own_log = (uint32_t)comm_log_world(comm);
+      g.own_rank = (uint32_t)comm_rank(comm);
+      bucket_lo = 0;
+      bucket_hi = g.half >> g.own_log;
+    }
   } else {
     comm = nullptr;
   }
@@ -780,7 +787,8 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
     for (uint32_t rho = 0; rho < world; rho++)
       for (uint32_t s = 0; s < g.sets; s++)
         fin[(size_t)rho * g.sets + s] = reduce_fold_final(raw.data() + (size_t)rho * per_rank + (size_t)s * m, m, log_G);
-    host_join_bucket_shards_strided(fin.data(), world, g.sets, ws.data());
+    if (g.own_log) host_join_bucket_shards_strided(fin.data(), world, g.sets, ws.data());
+    else host_join_bucket_shards(fin.data(), world, g.sets, g.nloc, ws.data());
   } else {
     std::vector<SR> raw((size_t)g.sets * m), fin(g.sets);
     PB_CUDA(cudaMemcpyAsync(raw.data(), cur, raw.size() * sizeof(SR), cudaMemcpyDeviceToHost, st));
