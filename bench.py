@@ -317,8 +317,12 @@ def b200_arm(args):
         """every active lane proves `steps` times, all lanes concurrently; returns per-lane host milliseconds"""
         def worker(lane):
             t_lane = time.perf_counter()
+            marks = []
             for _ in range(steps):
                 fn(lane)
+                marks.append(time.perf_counter())
+            if os.environ.get("PB200_BENCH_STEP_TIMES"):  # debugging aid: host clock of every step
+                print("    steps (ms):", [round((b - a) * 1e3, 1) for a, b in zip([t_lane] + marks[:-1], marks)], file=sys.stderr)
             return round((time.perf_counter() - t_lane) * 1e3, 1)
         active = lanes if active is None else active
         return [worker(active[0])] if len(active) == 1 else list(pool.map(worker, active))
@@ -397,19 +401,6 @@ def b200_arm(args):
             golden_match = bool(json.load(open(gpath))["proof_hex"] == ref_proof.hex())
         except Exception:
             golden_match = None
-
-    # outside every timed region: the proof that was timed is a valid proof -- the product's verifier (GPU linear
-    # combinations + the BN254 pairing against X2 = [tau]_2) accepts it and rejects a tampered copy
-    verified = None
-    if rank == 0 and not args.no_verify:
-        vk = setup.verification_key_arrays(n, pk)
-        pf = pb.Proof.from_bytes(ref_proof)
-        pub_ints = [int(x) for x in public]
-        bad = bytearray(ref_proof)
-        bad[32 * 14 + 31] ^= 1  # lowest bit of a_eval
-        verified = bool(vk.verify_proof(n, pf, pub_ints) and vk.verify_proof_unoptimized(n, pf, pub_ints)
-                        and not vk.verify_proof(n, pb.Proof.from_bytes(bytes(bad)), pub_ints))
-        assert verified, "the benchmarked proof does not verify"
 
     # ---- N > 1: ONE proof across all the GPUs (north_star's sharded path), checked and timed where the driver's
     # scaling run sees it: coset slices + slab-sharded interpolation + bucket-sharded commitments, the library's own
@@ -535,6 +526,20 @@ def b200_arm(args):
                 "nvlink_bytes_received_per_proof_and_rank": shard["bytes_received_per_proof"],
                 "note": "ONE proof / transform / commitment across all ranks (strong scaling), max over ranks, device "
                         "timed; full-vector in, full-vector out on every rank"}
+
+    # outside every timed region (and after every timed section: it runs on rank 0 only, on the library's default
+    # context): the proof that was timed is a valid proof -- the product's verifier (GPU linear
+    # combinations + the BN254 pairing against X2 = [tau]_2) accepts it and rejects a tampered copy
+    verified = None
+    if rank == 0 and not args.no_verify:
+        vk = setup.verification_key_arrays(n, pk)
+        pf = pb.Proof.from_bytes(ref_proof)
+        pub_ints = [int(x) for x in public]
+        bad = bytearray(ref_proof)
+        bad[32 * 14 + 31] ^= 1  # lowest bit of a_eval
+        verified = bool(vk.verify_proof(n, pf, pub_ints) and vk.verify_proof_unoptimized(n, pf, pub_ints)
+                        and not vk.verify_proof(n, pb.Proof.from_bytes(bytes(bad)), pub_ints))
+        assert verified, "the benchmarked proof does not verify"
 
     if rank != 0:
         if world > 1:

@@ -61,13 +61,23 @@ __global__ void k_gen_interpass(Fr* out, uint64_t rows, uint64_t cols, Fr w, Fr 
   }
 }
 
-// planes[j] (lo 16 B) and planes[count + j] (hi 16 B) of w^j, j < count
+// Position of local twiddle j inside its 16-byte plane: the higher 3-bit groups of j XOR-folded into the low three
+// bits.  A stage reads the entries (low + m 2^t0) 2^s: eight lanes with different `low` would otherwise hit multiples
+// of 8 entries -- one 16-byte column of the 128-byte wavefront -- and serialise 8-fold (ncu: 2.9 conflicts per element
+// and pass after the data tile had been swizzled).  A bijection on [0, count) for any power-of-two count >= 8.
+__host__ __device__ __forceinline__ uint32_t twiddle_slot(uint32_t j, uint32_t count) {
+  return count >= 8 ? j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u) : j;
+}
+
+// planes[slot(j)] (lo 16 B) and planes[count + slot(j)] (hi 16 B) of w^j, j < count: stored pre-swizzled so that the
+// TMA bulk copy of the kernel stays one linear transfer
 __global__ void k_gen_local(uint4* planes, uint32_t count, Fr w) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   Fr x = fp_pow_u64(w, j);
-  planes[j] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-  planes[count + j] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  const uint32_t t = twiddle_slot(j, count);
+  planes[t] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  planes[count + t] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
 
 // out[i] = scale * base^i
@@ -203,7 +213,7 @@ __device__ __forceinline__ void ntt_round8(uint4* s_lo, uint4* s_hi, const uint4
     for (int m = 0; m < (1 << s); m++) {
       Fr tw;
       const bool unit = (st == 0);
-      if (!unit) tw = ld_planes(t_lo, t_hi, (low + ((uint32_t)m << t0)) << (log_b - 1 - st));
+      if (!unit) tw = ld_planes(t_lo, t_hi, twiddle_slot((low + ((uint32_t)m << t0)) << (log_b - 1 - st), 1u << (log_b - 1)));
 #pragma unroll
       for (int h = 0; h < (4 >> s); h++) {
         const int k = m + (h << (s + 1));
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(PB_NTT_THREADS, PB_NTT_BLOCKS) k_ntt_pass(Pass
         uint32_t i1 = i0 + (half << p.log_cc);
         Fr u = ld_tile(s_lo, s_hi, i0, z);
         Fr v = ld_tile(s_lo, s_hi, i1, z);
-        if (t > 0) v = fp_mul(v, ld_planes(t_lo, t_hi, j << (p.log_b - 1 - t)));
+        if (t > 0) v = fp_mul(v, ld_planes(t_lo, t_hi, twiddle_slot(j << (p.log_b - 1 - t), TW)));
         st_tile(s_lo, s_hi, i0, fp_add(u, v), z);
         st_tile(s_lo, s_hi, i1, fp_sub(u, v), z);
       }

@@ -15,8 +15,27 @@ L = _lib.lib(); ctx = _lib.default_context()
 setup = pb.Setup.generate(0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF, n, ctx=ctx)
 c = syn.build_circuit(log_n, seed=20260924, n_public=2)
 pk, A, B, C, public = syn.circuit_arrays(c)
+mode = os.environ.get("PROBE_MODE", "")
+if "pinned" in mode:
+    A, B, C = (torch.from_numpy(x).pin_memory().numpy() for x in (A, B, C))
+if "extra" in mode:  # what bench.py has alive when it times the sharded proof: single-GPU provers on two contexts
+    extra = [pb.Prover.from_arrays(setup, n, pk), pb.Prover.from_arrays(setup, n, pk, ctx=_lib.Context(local))]
+    for e in extra:
+        e.prove_arrays(A, B, C, public)
+if "vk" in mode and rank == 0:  # what bench.py's verification does on rank 0 before the sharded section
+    vk = setup.verification_key_arrays(n, pk)
+    if "verify" in mode:
+        single = pb.Prover.from_arrays(setup, n, pk).prove_arrays(A, B, C, public)
+        print("verified:", vk.verify_proof(n, pb.Proof.from_bytes(single), [int(x) for x in public]), flush=True)
 sp = parallel.ShardedProver.from_arrays(setup, n, pk)
 ref = sp.prove_arrays(A, B, C, public)
+if "onecall" in mode:
+    for it in range(3):
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        sp.prove_arrays(A, B, C, public)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print("proof %d (one call): %.2f ms" % (it, (time.perf_counter() - t0) * 1e3), flush=True)
 for it in range(3):
     _lib.check(L.pb200_ctx_timing(ctx.handle, 1))
     dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter(); marks = []
