@@ -549,8 +549,8 @@ def b200_arm(args):
     proofs = args.steps * K * world
     value = proofs / (ms_dev * 1e-3)
     e2e = proofs / (ms_e2e * 1e-3)
-    # dominant kernel group: the MSM bucket accumulation (rounds of batched affine additions: k_aff_round0 +
-    # k_aff_round launches of one MSM call, bracketed by one event pair).  Algorithmic bytes: 96 B per point (64 B
+    # dominant kernel: the MSM bucket accumulation (k_msm_seg_accumulate, one launch per MSM call, bracketed by an
+    # event pair; with PB200_MSM_ACC=affine the rounds of batched affine additions of the call instead).  Algorithmic bytes: 96 B per point (64 B
     # affine point + 32 B scalar) x the points of the call.
     xyzz = os.environ.get("PB200_MSM_ACC") != "affine"
     acc_avg_ms = acc_ms / max(1, acc_cnt)
@@ -563,7 +563,7 @@ def b200_arm(args):
     traffic = None
     try:
         dk = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant_kernel.json")))
-        if dk.get("log_n") == log_n and not xyzz:
+        if dk.get("log_n") == log_n and xyzz:
             traffic = dk["dram_bytes_per_point"] * points_per_launch
     except Exception:
         pass
@@ -605,8 +605,8 @@ def b200_arm(args):
                                           "reduce": red_ms / args.steps},
                      "note": "a 'launch' is one MSM call's accumulation (event pair around its rounds), timed in a pass with "
                              "one lane (see config.step); integer-pipe bound, not HBM bound (ncu: profiles/); "
-                             "modmul_ceiling_frac = field products/s (6 per affine addition, one addition per point and "
-                             "window) / 65.4e9 measured peak; traffic exceeds the algorithmic bytes because every point "
+                             "modmul_ceiling_frac = field products/s (10 per XYZZ += affine addition -- 6 with "
+                             "PB200_MSM_ACC=affine --, one addition per point and window) / 65.4e9 measured peak; traffic exceeds the algorithmic bytes because every point "
                              "is gathered once per window from the fixed-base table: see DESIGN.md"},
         "roofline_ntt": {"bound": "hbm", "kernel": "k_ntt_pass", "launches": int(ntt_cnt), "avg_launch_ms": ntt_avg_ms,
                          "achieved": comp["fr_ntt_fwd_plus_inv_2^%d" % log_n]["roofline"]["achieved"], "peak": hbm_gbs,
