@@ -375,6 +375,25 @@ def test_prove_many_public_inputs_dense_path(pb):
     assert raw == O.proof_bytes(O.Prover(osetup, opk).prove(a, b, cc, c.public_values()))
 
 
+@pytest.mark.parametrize("log_n,n_public", [(12, 12), (13, 2)])
+def test_prove_mid_size_vs_oracle(pb, log_n, n_public):
+    """mid-size differential against the oracle prover (its fft / ec_lincomb answered by the C restatement,
+    oracle/fast.py -- byte-identical to the pure-Python oracle, tests/test_oracle_fast.py): the two-pass NTT regime
+    (4n = 2^14, 2^15: tiles of several columns), and more than 8 public inputs through the interpolated-PI branch at a size where it
+    crosses tile boundaries"""
+    from oracle import fast as F
+    from plonkathon_b200 import synthetic as syn
+    n = 1 << log_n
+    c = syn.build_circuit(log_n, seed=40 + log_n, n_public=n_public)
+    pk, A, B, C, public = syn.circuit_arrays(c)
+    setup = pb.Setup.generate(TAU, n)
+    raw = pb.Prover.from_arrays(setup, n, pk).prove_arrays(A, B, C, public)
+    S1, S2, S3 = syn.permutation_polys(c.wire_L, c.wire_R, c.wire_O, n, c.n_constraints)
+    opk = O.Preprocessed(n, c.QM, c.QL, c.QR, c.QO, c.QC, S1, S2, S3)
+    a, b, cc = c.wires_values()
+    assert raw == O.proof_bytes(F.prove(F.Setup(TAU, n), opk, a, b, cc, c.public_values()))
+
+
 def test_verification_key_object(pb, setup):
     """Setup.verification_key(pk) (setup.py:75-77) with a CommonPreprocessedInput-shaped object"""
     from collections import namedtuple
