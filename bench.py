@@ -355,7 +355,15 @@ def b200_arm(args):
     if os.environ.get("PB200_BENCH_NO_SAMPLER"):  # debugging aid: leaves "clocks" unavailable
         sampler.nvml, sampler._sample_smi = None, (lambda: (_ for _ in ()).throw(RuntimeError("disabled")))
     sampler.start()  # started (and NVML initialised) before the warm-up; records only inside the timed regions
+    if world > 1:
+        # the first collectives on torch's communicator initialise NCCL lazily (channels, proxy threads, buffer
+        # registration) and were seen to stall one rank's CUDA calls for ~150 ms afterwards: take that here, not in a
+        # timed region
+        warm = torch.ones(1, device="cuda")
+        dist.all_reduce(warm, op=dist.ReduceOp.MAX)
+        barrier()
     run_lanes(prove_device, args.warmup)
+    barrier()
     ref_proof = proof.raw
     sampler.recording.set()  # sampling is already running during this last untimed step: nothing about it is new
     run_lanes(prove_host, 1)  # to the driver when the timed region starts
