@@ -374,6 +374,15 @@ def b200_arm(args):
     ms_dev = timed(prove_device, args.steps)
     launches = sum(lane["ctx"].launches for lane in lanes) - launches0
     ms_e2e = timed(prove_host, args.steps)
+    # The device-resident path does strictly less than the host-buffer path.  A reading more than 25 % ABOVE it means the
+    # first timed region was hit by a one-off stall (seen once on rank 0 of an 8-GPU run: 369 ms against 219 ms on the
+    # other seven ranks and in the e2e region right after): re-measure it once, as for a throttled run, and say so.
+    remeasured = None
+    if ms_dev > 1.25 * ms_e2e:
+        remeasured = {"first_reading_ms": ms_dev, "reason": "device-resident region slower than the host-buffer region"}
+        launches0 = sum(lane["ctx"].launches for lane in lanes)
+        ms_dev = timed(prove_device, args.steps, name="prove_device (re-measured)")
+        launches = sum(lane["ctx"].launches for lane in lanes) - launches0
     sampler.recording.clear()
     sampler.stop_flag.set()
     sampler.join(timeout=2)
@@ -592,6 +601,7 @@ def b200_arm(args):
         "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": K * (3 * n * 32 + 32 * len(public)),
                 "d2h_bytes_per_step": K * 768, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "value_remeasured": remeasured,
         "proof_verified": verified,
         "proof_matches_oracle_golden": golden_match,
         "sharded_proof_matches_single": shard["proof_ok"] if shard else None,
