@@ -644,8 +644,9 @@ def b200_arm(args):
             line["cpu_baseline"] = {
                 "value": 1.0 / (t * scale), "unit": "proofs/s", "cores": 1, "kind": "port",
                 "sample": "oracle port of the reference's Python path: Prover.prove at 2^%d gates took %.2f s on one "
-                          "host core, scaled linearly in gates to 2^%d (host has %d cores; the reference is "
-                          "single-threaded)" % (args.cpu_log_n, t, log_n, os.cpu_count() or 0)}
+                          "host core, scaled linearly in gates to 2^%d (%d usable host cores; the reference is "
+                          "single-threaded; --impl reference runs one worker per usable core)"
+                          % (args.cpu_log_n, t, log_n, usable_cores())}
         except Exception as e:  # the bench line must still print
             line["cpu_baseline"] = {"value": None, "unit": "proofs/s", "cores": 1, "kind": "port", "sample": "failed: %r" % e}
     if not args.no_cpu_baseline:
