@@ -11,8 +11,13 @@ A "step" is one full proof (Prover.prove rounds 1-5, 9 KZG commitments) of a syn
   e2e   : proofs/s through the reference-facing C ABI call with HOST buffers (pb200_prover_prove): the three
           wire-value vectors are copied host->device from pinned memory and the 768-byte proof is read back
           inside the timed region, every step.
-N > 1: one process per GPU (torchrun), every rank proves its own copy of the circuit (proofs are
-independent units: no data-path collective); value = N*K proofs / max-over-ranks time ("weak")."""
+N > 1: one process per GPU (torchrun).  `value` / `e2e`: every rank proves its own copy of the circuit (proofs are
+independent units: no data-path collective); value = N*K*lanes proofs / max-over-ranks time ("weak").  The same run
+then proves ONE instance across all ranks (plonkathon_b200.parallel.ShardedProver: coset slices, slab-sharded
+transforms, bucket-sharded commitments, the library's own NCCL allgathers at the joins), checks it byte for byte
+against the single-GPU proof, times it, and does the same for the sharded NTT and the sharded commitment as
+operators: `one_proof_sharded`, `sharded_proof_matches_single`, `slab_ntt_matches_single`,
+`sharded_msm_matches_single` and `components.sharded_across_N_gpus` in the JSON line."""
 import argparse
 import ctypes
 import json
