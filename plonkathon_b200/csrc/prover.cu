@@ -93,6 +93,30 @@ __device__ __forceinline__ Fr ldg_fr(const Fr* p) {
   return r;
 }
 
+static Fr load_fr_checked(const uint8_t* h) {
+  Fr a;
+  memcpy(a.v, h, 32);
+  const Fr m = Fr::modulus();
+  bool lt = false;
+  for (int i = 7; i >= 0; i--) {
+    if (a.v[i] != m.v[i]) { lt = a.v[i] < m.v[i]; break; }
+  }
+  PB_CHECK(lt, "public input not reduced below the field modulus");
+  return a;
+}
+
+// wire values arrive canonical (< r): a value >= r would silently become a different field element in fp_to_mont
+__global__ void k_count_noncanonical(const Fr* v, uint64_t n, uint32_t* bad) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr x = ldg_fr(v + i), m = Fr::modulus();
+  bool lt = false;
+  for (int l = 7; l >= 0; l--) {
+    if (x.v[l] != m.v[l]) { lt = x.v[l] < m.v[l]; break; }
+  }
+  if (!lt) atomicAdd(bad, 1u);
+}
+
 // prover.py:108-116: A*QL + B*QR + A*B*QM + C*QO + PI + QC == 0 on every row
 __global__ void k_gate_check(const Fr* A, const Fr* B, const Fr* C, const Fr* QL, const Fr* QR, const Fr* QM,
                              const Fr* QO, const Fr* QC, const Fr* PI, uint64_t n, uint32_t* bad) {
@@ -624,8 +648,14 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     PB_CUDA(cudaStreamWaitEvent(st, ctx->aux_ev[2], 0));
   }
   const uint8_t* src[3] = {hA, hB, hC};
+  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));  // [0] gate check, [1] wire values not reduced below r
+  for (uint64_t i = 0; i < n_public; i++) (void)load_fr_checked(h_public + 32 * i);
   if (wires_on_device) {
-    for (int k = 0; k < 3; k++) fr_to_mont(ctx, reinterpret_cast<const Fr*>(src[k]), P->lag[k].as<Fr>(), n);
+    for (int k = 0; k < 3; k++) {
+      k_count_noncanonical<<<PB_GRID(n, 256), 0, st>>>(reinterpret_cast<const Fr*>(src[k]), n, P->flags.as<uint32_t>() + 1);
+      fr_to_mont(ctx, reinterpret_cast<const Fr*>(src[k]), P->lag[k].as<Fr>(), n);
+    }
+    ctx->launches += 3;
   } else {
     // stage the three wire vectors on a copy stream so the transfers of B and C overlap the conversion and
     // transform of the previous vector (the copy engine runs beside the SMs)
@@ -646,6 +676,8 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     for (int k = 0; k < 3; k++) {
       PB_CUDA(cudaStreamWaitEvent(st, ctx->copy_done[k], 0));
       if (P->world > 1) comm_allgather_inplace(ctx_comm(ctx), P->lag[k].p, slab * 32, st);
+      k_count_noncanonical<<<PB_GRID(n, 256), 0, st>>>(P->lag[k].as<Fr>(), n, P->flags.as<uint32_t>() + 1);
+      ctx->launches++;
       fr_to_mont(ctx, P->lag[k].as<Fr>(), P->lag[k].as<Fr>(), n);
       if (P->world == 1) ntt_run(ctx, P->lag[k].as<Fr>(), P->coeff[k].as<Fr>(), P->log_n, true, n, nullptr, nullptr);
     }
@@ -660,7 +692,6 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     k_negate<<<PB_GRID(n_public, 128), 0, st>>>(P->pi_lag.as<Fr>(), n_public);
     ctx->launches++;
   }
-  PB_CUDA(cudaMemsetAsync(P->flags.p, 0, 64, st));
   k_gate_check<<<PB_GRID(n, 128), 0, st>>>(P->lag[0].as<Fr>(), P->lag[1].as<Fr>(), P->lag[2].as<Fr>(),
                                           P->sel_lag[Prover::QL].as<Fr>(), P->sel_lag[Prover::QR].as<Fr>(),
                                           P->sel_lag[Prover::QM].as<Fr>(), P->sel_lag[Prover::QO].as<Fr>(),
@@ -684,7 +715,11 @@ void prover_round1(Prover* P, const uint8_t* hA, const uint8_t* hB, const uint8_
     Fr* pc = P->coeff[4].as<Fr>();
     interpolate(P, &pl, &pc, 1);
   }
-  PB_CHECK(read_flag(P, 0) == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
+  uint32_t fl[2];
+  PB_CUDA(cudaMemcpyAsync(fl, P->flags.p, 8, cudaMemcpyDeviceToHost, st));
+  PB_CUDA(cudaStreamSynchronize(st));
+  PB_CHECK(fl[1] == 0, "wire value not reduced below the field modulus (canonical 32-byte little-endian expected)");
+  PB_CHECK(fl[0] == 0, "AssertionError: witness does not satisfy the gate constraints (prover.py:108-116)");
   if (P->overlap) launch_coset_ext_async(P, 0, 3, 0);
   const Fr* abc[3] = {P->coeff[0].as<Fr>(), P->coeff[1].as<Fr>(), P->coeff[2].as<Fr>()};
   P->commit_batch(abc, 3, n, P->proof.pts[0]);

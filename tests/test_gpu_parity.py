@@ -467,6 +467,29 @@ def test_error_behaviour_matches_reference(pb, setup):
     assert pb.ec_mul(None, 5) is None and pb.ec_lincomb([(g, 0)]) is None
 
 
+def test_prove_rejects_non_canonical_arrays(pb, setup):
+    """array inputs are canonical 32-byte little-endian field elements: a wire value or a public input >= r is refused
+    (the list-of-ints surface reduces mod r like the reference's Scalar(...); raw arrays cannot be reduced silently)"""
+    entry, arr = load_circuit("factorization")
+    n = entry["n"]
+    prover = pb.Prover.from_arrays(setup, n, _pk(arr))
+    good = prover.prove_arrays(arr["A"], arr["B"], arr["C"], ints(entry["public"]))
+    rows = lambda v: np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in v), dtype=np.uint8).reshape(-1, 32).copy()  # noqa: E731
+    A = rows(arr["A"])
+    A = np.concatenate([A, np.zeros((n - A.shape[0], 32), dtype=np.uint8)])
+    bad = A.copy()
+    bad[1] = np.frombuffer((int.from_bytes(bytes(A[1]), "little") + R).to_bytes(32, "little"), dtype=np.uint8)  # same residue, not reduced
+    from plonkathon_b200._lib import PlonkB200Error
+    with pytest.raises(PlonkB200Error, match="not reduced"):
+        prover.prove_arrays(bad, arr["B"], arr["C"], ints(entry["public"]))
+    pub = rows(ints(entry["public"]))
+    pub_bad = pub.copy()
+    pub_bad[0] = np.frombuffer((int.from_bytes(bytes(pub[0]), "little") + R).to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(PlonkB200Error, match="not reduced"):
+        prover.prove_arrays(A, arr["B"], arr["C"], pub_bad)
+    assert prover.prove_arrays(A, arr["B"], arr["C"], pub) == good  # the prover object is fine afterwards
+
+
 def test_prove_2p22_gates_runs(pb):
     """BASELINE.json's largest configuration size (2^22 gates, 4n = 2^24 domain) on one GPU: the proof is
     deterministic and its commitments are on the curve (full verification is covered at 2^20)."""
