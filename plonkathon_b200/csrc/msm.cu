@@ -7,17 +7,22 @@
 //      with a global histogram of bucket loads                                  (k_msm_histogram)
 //   2. exclusive scan of the histogram                                           (k_scan_*)
 //   3. counting-sort scatter of (point index, sign) by bucket                    (k_msm_scatter)
-//   4. bucket accumulation by rounds of pairwise batched-AFFINE additions, one safegcd inversion per thread
-//      and round: 6 field products per addition (msm_bucket.cuh)               (k_aff_round0 / k_aff_round / k_aff_tail)
-//      [A/B alternative, PB200_MSM_ACC=xyzz: XYZZ accumulators over fixed segments of the sorted entries,
-//       10 products per addition                                      (k_msm_seg_accumulate, k_msm_stitch[_heavy])]
-//   5. bucket reduction sum_b (b+1) * B_b by recursive grouped running sums, one thread per group at every
-//      level                                                                     (k_reduce_level0 / k_reduce_level)
-//   6. the few remaining group operations (bucket-range offset, window Horner, one inversion to affine) on the
-//      host, which has to read the point anyway to feed the Fiat-Shamir transcript.
-// Multi-GPU: a rank may own a BUCKET RANGE [bucket_lo, bucket_hi) of every bucket set -- it walks all digits but
-// sorts, accumulates and reduces only its own buckets, so the whole MSM (not just the accumulation) divides by the
-// number of ranks; or a POINT RANGE (a sub-vector of the points).  Either way it returns XYZZ partial sums.
+//   4. load-balanced bucket accumulation over fixed segments of the sorted entries: XYZZ accumulator += affine
+//      point (8M+2S, no inversion), SIMT-uniform loop                            (k_msm_seg_accumulate)
+//      + stitching of buckets that cross a segment boundary, block trees for heavy ones, piece-wise for buckets of
+//      more than 1024 segments                                                   (k_msm_stitch[_pieces|_heavy])
+//      [A/B alternative, PB200_MSM_ACC=affine: rounds of pairwise batched-affine additions, one safegcd inversion
+//       per thread and round, 6 products per addition -- measured slower        (k_aff_round0 / k_aff_round / k_aff_tail)]
+//   5. bucket reduction sum_b (b+1) * B_b by recursive grouping: running sums over 16 buckets per thread, then
+//      block-wide suffix-scan levels over 512 elements                           (k_reduce_level0 / k_reduce_block)
+//   6. the few remaining group operations (last <= 8 reduction pairs, bucket-range offset or the join of the ranks'
+//      shares, window Horner, one inversion to affine) on the host, which has to read the point anyway to feed the
+//      Fiat-Shamir transcript.
+// Multi-GPU: a call may own a sub-range of the buckets of every bucket set -- contiguous [bucket_lo, bucket_hi), or,
+// with a communicator, every G-th bucket -- it walks all digits but sorts, accumulates and reduces only its own
+// buckets, so the whole MSM (not just the accumulation) divides by the number of ranks; and/or a POINT RANGE (a
+// sub-vector of the points).  It then returns partial sums; with a communicator the (S, R) pairs of the ranks are
+// exchanged with one allgather and every rank returns the full result.
 // Two modes: "generic" (arbitrary points: W windows x 2^(c-1) buckets) and "fixed-base" (SRS with the
 // window multiples 2^(c*w) * P_i precomputed in HBM: one shared set of 2^(c-1) buckets, no Horner).
 #include <algorithm>
@@ -725,8 +730,7 @@ void msm_run_batch(Context* ctx, const G1Affine* points, uint64_t n, const Fr* c
                                                      own_slot, buckets.as<G1XYZZ>(), heavy, heavy_count, pieces, 16);
     k_msm_stitch_pieces<<<std::min<uint32_t>(max_pieces, 592), 128, 0, st>>>(slots, heavy, heavy_count, pieces, piece_partial);
     k_msm_stitch_heavy<<<296, 128, 0, st>>>(slots, heavy, heavy_count, piece_partial, buckets.as<G1XYZZ>());
-    ctx->launches += 1;
-    ctx->launches += 3;
+    ctx->launches += 4;
     ra.xb = buckets.as<G1XYZZ>();
   }
 
