@@ -1,8 +1,11 @@
-// Bucket accumulation and bucket reduction of the G1 MSM (msm.cu): the thread bodies.
+// Bucket reduction of the G1 MSM (msm.cu) and the batched-affine alternative for its bucket accumulation: the
+// thread bodies.
 //
 // Replaces the additions of curve.py:38-111 (`ec_lincomb` over py_ecc `add`, one field inversion per addition).
 //
-// Accumulation = rounds of pairwise AFFINE additions that share one inversion per thread (Montgomery's trick):
+// Accumulation, `PB200_MSM_ACC=affine` only (the default is the XYZZ segment kernel in msm.cu; this one is exact
+// but measured slower on B200, profiles/r02_msm_affine_vs_xyzz.md) = rounds of pairwise AFFINE additions that share
+// one inversion per thread (Montgomery's trick):
 // 6 field products per addition (1 forward, 5 backward) instead of 10 for an XYZZ += affine step, plus one
 // safegcd inversion (modinv.cuh, no multiplication chain) amortised over the B additions of a thread.
 //
