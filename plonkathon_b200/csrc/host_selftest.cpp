@@ -6,6 +6,7 @@
 #include "msm_digits.cuh"
 #include "modinv.cuh"
 #include "msm_bucket.cuh"
+#include "ntt_shard.cuh"
 #include <vector>
 #include <cstring>
 using namespace pb200;
@@ -37,6 +38,28 @@ int hs_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_
     st(out, r);                                                  \
   }
   if (field == 0) RUN(Fr) else RUN(Fq)
+  return 0;
+}
+
+// The join of the slab-sharded NTT (ntt_shard.cuh): out[k] = sum_r x[r] w^(r k) for G = 2^log_g elements in Montgomery
+// form, tw = w^0 .. w^(G/2 - 1) (Montgomery).  x, out: G x 8 limbs; tw: 4 x 8 limbs.
+int hs_small_dft(int log_g, const uint32_t* x, const uint32_t* tw, uint32_t* out) {
+  DftTw t;
+  for (int k = 0; k < 4; k++) t.w[k] = ld<Fr>(tw + 8 * k);
+#define RUN_DFT(LG)                                                     \
+  {                                                                     \
+    Fr v[1 << LG];                                                      \
+    for (int i = 0; i < (1 << LG); i++) v[i] = ld<Fr>(x + 8 * i);       \
+    small_dft<LG>(v, t);                                                \
+    for (int i = 0; i < (1 << LG); i++) st(out + 8 * i, v[i]);          \
+  }
+  switch (log_g) {
+    case 1: RUN_DFT(1) break;
+    case 2: RUN_DFT(2) break;
+    case 3: RUN_DFT(3) break;
+    default: return -1;
+  }
+#undef RUN_DFT
   return 0;
 }
 

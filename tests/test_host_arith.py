@@ -20,7 +20,7 @@ def lib():
     out = os.path.join(ROOT, "build", "host_selftest.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(CSRC, "host_selftest.cpp")
-    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "msm_digits.cuh", "msm_bucket.cuh", "modinv.cuh")]
+    deps = [src] + [os.path.join(CSRC, h) for h in ("field.cuh", "curve.cuh", "msm_digits.cuh", "msm_bucket.cuh", "modinv.cuh", "ntt_shard.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src,
                                "-I", CSRC, "-o", out])
@@ -130,6 +130,24 @@ def test_curve_ops(lib):
         o5 = (ctypes.c_uint32 * 32)()
         lib.hs_curve_op(2, o3, limbs(0, 4), 0, o5)
         assert to_affine(lib, o5) == to_affine(lib, o4)
+
+
+@pytest.mark.parametrize("log_g", [1, 2, 3])
+def test_sharded_ntt_join_dft(lib, log_g):
+    """csrc/ntt_shard.cuh small_dft: the G-point DFT over the rank index at the join of the slab-sharded NTT, as the
+    kernel instantiates it (bit-reversed input, radix-2 butterflies in registers), against the definition -- forward and
+    inverse roots"""
+    rng = random.Random(log_g)
+    p, G = O.R_MOD, 1 << log_g
+    mont = lambda v: v * R256 % p  # noqa: E731
+    for w in (pow(O.root_of_unity(64), 64 // G, p), pow(O.root_of_unity(64), -(64 // G), p)):
+        x = [rng.randrange(p) for _ in range(G)]
+        xb = (ctypes.c_uint32 * (8 * G))(*[(mont(v) >> (32 * i)) & 0xFFFFFFFF for v in x for i in range(8)])
+        tw = (ctypes.c_uint32 * 32)(*[(mont(pow(w, k, p)) >> (32 * i)) & 0xFFFFFFFF for k in range(4) for i in range(8)])
+        out = (ctypes.c_uint32 * (8 * G))()
+        assert lib.hs_small_dft(log_g, xb, tw, out) == 0
+        got = [unlimbs(out, k) * pow(R256, -1, p) % p for k in range(G)]
+        assert got == [sum(x[r] * pow(w, r * k, p) for r in range(G)) % p for k in range(G)]
 
 
 def test_msm_signed_digit_slicing(lib):
