@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=20260924, help="seed of the synthetic circuit (7 with --log-n 22 is the "
                     "circuit of tests/golden/proof_2p22.json)")
     ap.add_argument("--cpu-log-n", type=int, default=8, help="size of the bounded CPU sample (2^k gates)")
-    ap.add_argument("--cpu-fit", default="6,8,10", help="reference arm: sample sizes (log2 gates) of the cost fit")
+    ap.add_argument("--cpu-fit", default="5,7,9", help="reference arm: sample sizes (log2 gates) of the cost fit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0,
                     help="reference arm: worker processes proving independent instances side by side "
