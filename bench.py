@@ -151,7 +151,8 @@ def reference_arm(args):
     cores = usable_cores()
     procs = min(256, args.cpu_procs if args.cpu_procs > 0 else cores)
     sizes = sorted({int(x) for x in args.cpu_fit.split(",") if x})
-    t_single = cpu_sample(min(8, max(sizes)), 1)[1][0] if procs > 1 else None  # one process alone, for the slowdown
+    k8 = sizes[len(sizes) // 2]  # the middle sample size: one process alone against all workers running
+    t_single = cpu_sample(k8, 1)[1][0] if procs > 1 else None
     job = (sizes, 1 if args.warmup > 0 else 0, args.steps)
     per_proc = None
     if procs > 1:
@@ -169,8 +170,7 @@ def reference_arm(args):
     n_full = 1 << args.log_n
     t_full = a * n_full + b * n_full * args.log_n          # seconds per 2^log_n-gate proof in one worker
     value = procs / t_full                                  # all workers
-    k8 = min(8, max(sizes))
-    slowdown = (mean_t[k8] / t_single) if (t_single and k8 in mean_t) else 1.0
+    slowdown = (mean_t[k8] / t_single) if t_single else 1.0
     sample = ("%d worker processes on %d usable host cores (os.cpu_count() = %s), each running the oracle port of "
               "Prover.prove on 2^{%s}-gate instances of the same synthetic circuit family: %s s per proof and worker; "
               "cost model t(n) = a n + b n log2 n fitted to those points (a = %.3e, b = %.3e) and EXTRAPOLATED to "
