@@ -658,6 +658,10 @@ void ntt_shard_local(Context* ctx, const Fr* const* in, int count, int log_n, bo
 void ntt_sharded(Context* ctx, const Fr* const* in, Fr* const* out, int count, int log_n, bool inverse) {
   Comm* cm = ctx_comm(ctx);
   const int log_g = comm_log_world(cm), rank = comm_rank(cm), G = 1 << log_g;
+  if (G == 1) {  // a communicator of one rank: nothing to shard
+    for (int v = 0; v < count; v++) ntt_run(ctx, in[v], out[v], log_n, inverse, (uint64_t)1 << log_n, nullptr, nullptr);
+    return;
+  }
   const uint64_t M = (uint64_t)1 << (log_n - log_g);
   ntt_shard_local(ctx, in, count, log_n, inverse, (uint64_t)G, (uint64_t)rank);
   for (int v = 0; v < count; v++)
